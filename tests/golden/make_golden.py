@@ -1,0 +1,234 @@
+"""Generates tests/golden/*.npz from the REFERENCE itself (run in the build container only).
+
+Sources of truth used here (nothing from this repo's product or oracle code):
+  * oracle/_ref/pet_ref_cpu.so  = unmodified /root/reference/pet/lib/ops/csrc/ROIAlign/ROIAlign_cpu.cpp and
+    NMS/soft_nms.cpp compiled in place by oracle/build_ref.py;
+  * the reference's own Python (imported from /root/reference with the four shims of SURVEY.md 8c):
+    pet/rcnn/utils/poolers.py (LevelMapper, Pooler), pet/utils/data/structures/bounding_box.py (BoxList),
+    pet/rcnn/modeling/grid_cascade_rcnn/inference.py (GridPostProcessor.get_boxes);
+  * torchvision 0.26 CPU `nms` (the third-party op behind pet/lib/ops/nms.py:2,10).
+
+    python tests/golden/make_golden.py          # rewrites the fixtures (seeded, deterministic)
+
+/root/reference does not exist on the GPU box; the committed .npz files are what travels.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torchvision
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import build_ref  # noqa: E402
+
+LEVEL_SHAPES = [(50, 84), (25, 42), (13, 21), (7, 11)]       # a 200x336 image at strides 4..32
+SCALES = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+IMG_H, IMG_W = 200, 336
+
+
+def install_shims(ref_ops):
+    apex = types.ModuleType("apex")
+    amp = types.ModuleType("apex.amp")
+    amp.float_function = lambda f: f
+    apex.amp = amp
+    sys.modules["apex"], sys.modules["apex.amp"] = apex, amp
+
+    class _FakeC(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            if hasattr(ref_ops, k):
+                return getattr(ref_ops, k)
+            return lambda *a, **kw: (_ for _ in ()).throw(RuntimeError("not built: _C." + k))
+
+    sys.modules["pet.lib.ops._C"] = _FakeC("pet.lib.ops._C")
+    for n, t in (("float", float), ("int", int), ("bool", bool)):
+        if not hasattr(np, n):
+            setattr(np, n, t)
+    import yaml
+    _yl = yaml.load
+    yaml.load = lambda s, Loader=None: _yl(s, Loader=Loader or yaml.FullLoader)
+    pc = types.ModuleType("pycocotools")
+    sys.modules["pycocotools"] = pc
+    for sub in ("mask", "coco", "cocoeval"):
+        m = types.ModuleType("pycocotools." + sub)
+        sys.modules["pycocotools." + sub] = m
+        setattr(pc, sub, m)
+    sys.modules["pycocotools.coco"].COCO = object
+    sys.modules["pycocotools.cocoeval"].COCOeval = object
+    # decode calls .cuda()/.get_device() unconditionally (inference.py:193,278)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def coco_like_rois(gen, n, img_h, img_w, n_img):
+    """SURVEY.md 8(d) RoI generator (sqrt(area) log-uniform, aspect log-uniform) + adversarial rows."""
+    s = torch.exp(torch.empty(n).uniform_(np.log(8.0), np.log(0.9 * min(img_h, img_w)), generator=gen))
+    ar = torch.exp(torch.empty(n).uniform_(np.log(0.5), np.log(2.0), generator=gen))
+    w = (s * torch.sqrt(ar)).clamp(max=img_w - 1)
+    h = (s / torch.sqrt(ar)).clamp(max=img_h - 1)
+    x1 = torch.rand(n, generator=gen) * (img_w - 1 - w)
+    y1 = torch.rand(n, generator=gen) * (img_h - 1 - h)
+    img = torch.randint(0, n_img, (n,), generator=gen).float()
+    rois = torch.stack([img, x1, y1, x1 + w, y1 + h], 1)
+    adv = torch.tensor([
+        [0, 0, 0, img_w - 1, img_h - 1],           # whole image
+        [1, -20, -30, 40, 50],                     # sticks out top-left
+        [0, img_w - 30, img_h - 20, img_w + 60, img_h + 45],   # sticks out bottom-right
+        [1, 100, 100, 100, 100],                   # zero area
+        [0, 50.25, 60.5, 50.75, 61.0],             # sub-pixel
+        [1, 10, 10, 12, 150],                      # thin, tall
+        [0, 5, 90, 330, 93],                       # thin, wide
+        [1, img_w + 200, img_h + 200, img_w + 300, img_h + 300],   # fully outside
+    ], dtype=torch.float32)
+    return torch.cat([rois, adv], 0)
+
+
+def gen_roi_align(ref):
+    g = torch.Generator().manual_seed(1234)
+    B, C = 2, 3
+    feats = [torch.randn(B, C, h, w, generator=g) for (h, w) in LEVEL_SHAPES]
+    rois = coco_like_rois(g, 32, IMG_H, IMG_W, B)
+    out = {"rois": rois.numpy()}
+    for l, f in enumerate(feats):
+        out["feat%d" % l] = f.numpy()
+    # (tag, PH, PW, sampling_ratio, aligned, levels)
+    cases = [("p7s2", 7, 7, 2, False, [0, 1, 2, 3]), ("p14s2", 14, 14, 2, False, [0, 2]),
+             ("p7s0", 7, 7, 0, False, [1]), ("p7s2a", 7, 7, 2, True, [1, 3]), ("p5x3s3", 5, 3, 3, False, [2])]
+    valid_aligned = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])
+    for tag, ph, pw, sr, al, levels in cases:
+        r = rois[valid_aligned] if al else rois
+        out["%s_sel" % tag] = np.nonzero(valid_aligned.numpy() if al else np.ones(len(rois), bool))[0]
+        for l in levels:
+            f = feats[l]
+            o = ref.roi_align_forward(f, r, SCALES[l], ph, pw, sr, al, 0)
+            go = torch.randn(o.shape, generator=g)
+            gi = ref.roi_align_backward(go, r, SCALES[l], ph, pw, B, C, f.shape[2], f.shape[3], sr, al, 0)
+            out["%s_l%d_out" % (tag, l)] = o.numpy()
+            out["%s_l%d_gout" % (tag, l)] = go.numpy()
+            out["%s_l%d_gin" % (tag, l)] = gi.numpy()
+    np.savez_compressed(os.path.join(HERE, "roi_align.npz"), **out)
+    return feats, rois
+
+
+def gen_pooler(feats, rois):
+    """The reference Pooler (poolers.py:43-132) end to end on CPU, its ROIAlign bound to the reference CPU op."""
+    from pet.rcnn.utils.poolers import Pooler, LevelMapper
+    from pet.utils.data.structures.bounding_box import BoxList
+    out = {}
+    boxlists = []
+    for i in range(feats[0].shape[0]):
+        sel = rois[:, 0] == i
+        boxlists.append(BoxList(rois[sel][:, 1:].clone(), (IMG_W, IMG_H), mode="xyxy"))
+    order = torch.cat([torch.nonzero(rois[:, 0] == i).squeeze(1) for i in range(feats[0].shape[0])])
+    out["order"] = order.numpy()
+    lm = LevelMapper(2, 5)
+    out["levels"] = lm(boxlists).numpy()
+    for tag, res in (("p7", (7, 7)), ("p14", (14, 14))):
+        pooler = Pooler("ROIAlign", res, SCALES, 2)
+        fs = [f.clone().requires_grad_(True) for f in feats]
+        y = pooler(fs, boxlists)
+        g = torch.Generator().manual_seed(7)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        out[tag + "_out"] = y.detach().numpy()
+        out[tag + "_gout"] = go.numpy()
+        for l, f in enumerate(fs):
+            out["%s_gin%d" % (tag, l)] = f.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "pooler.npz"), **out)
+
+
+def gen_levels():
+    from pet.rcnn.utils.poolers import LevelMapper
+    from pet.utils.data.structures.bounding_box import BoxList
+    g = torch.Generator().manual_seed(99)
+    n = 4000
+    s = torch.exp(torch.empty(n).uniform_(np.log(2.0), np.log(1500.0), generator=g))
+    ar = torch.exp(torch.empty(n).uniform_(np.log(0.2), np.log(5.0), generator=g))
+    w, h = s * torch.sqrt(ar), s / torch.sqrt(ar)
+    x1, y1 = torch.rand(n, generator=g) * 800, torch.rand(n, generator=g) * 800
+    boxes = torch.stack([x1, y1, x1 + w, y1 + h], 1)
+    # exact canonical boundaries: sqrt(area) = 112, 224, 448 with the +1 convention
+    exact = torch.tensor([[0, 0, 111, 111], [0, 0, 223, 223], [0, 0, 447, 447], [0, 0, 55, 55], [3, 4, 3, 4]],
+                         dtype=torch.float32)
+    boxes = torch.cat([boxes, exact], 0)
+    lv = LevelMapper(2, 5)([BoxList(boxes, (2000, 2000), mode="xyxy")])
+    np.savez_compressed(os.path.join(HERE, "levels.npz"), boxes=boxes.numpy(), levels=lv.numpy())
+
+
+def gen_nms(ref):
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    n = 700
+    base = torch.rand(n // 3 + 1, 2, generator=g) * 500
+    wh = torch.rand(n // 3 + 1, 2, generator=g) * 150 + 4
+    b0 = torch.cat([base, base + wh], 1)
+    boxes = torch.cat([b0 + torch.randn(b0.shape, generator=g) * s for s in (0.0, 4.0, 10.0)], 0)[:n]
+    boxes[5] = torch.tensor([10., 10., 10., 10.])      # zero-area pair: IoU = 0/0 = NaN -> never suppressed
+    boxes[6] = torch.tensor([10., 10., 10., 10.])
+    perm = torch.randperm(n, generator=g)
+    scores = (perm.float() + 0.5) / n                  # tie-free
+    labels = torch.randint(1, 6, (n,), generator=g)
+    out.update(boxes=boxes.numpy(), scores=scores.numpy(), labels=labels.numpy())
+    for thr in (0.3, 0.5, 0.7):
+        keep = torchvision.ops.nms(boxes, scores, thr)
+        out["nms_keep_%02d" % int(thr * 10)] = keep.numpy()
+        # reference soft_nms in hard mode (NMS/soft_nms.cpp) is a second CPU oracle for the keep SET
+        _, _, sk = ref.soft_nms(boxes.clone(), scores.clone(), 0.5, thr, 1e-4, 0)
+        out["softnms_hard_keep_%02d" % int(thr * 10)] = np.sort(sk.numpy())
+        # label-gated ml_nms = per-class torchvision nms merged by descending score
+        parts = []
+        for c in labels.unique():
+            idx = torch.nonzero(labels == c).squeeze(1)
+            parts.append(idx[torchvision.ops.nms(boxes[idx], scores[idx], thr)])
+        allk = torch.cat(parts)
+        allk = allk[torch.argsort(scores[allk], descending=True)]
+        out["mlnms_keep_%02d" % int(thr * 10)] = allk.numpy()
+    # ties: equal scores -> torchvision's stable sort keeps the lower index first
+    tscores = torch.round(scores * 20) / 20
+    out["tie_scores"] = tscores.numpy()
+    out["tie_keep_05"] = torchvision.ops.nms(boxes, tscores, 0.5).numpy()
+    np.savez_compressed(os.path.join(HERE, "nms.npz"), **out)
+
+
+def gen_decode():
+    from pet.rcnn.modeling.grid_cascade_rcnn.inference import GridPostProcessor
+    from pet.utils.data.structures.bounding_box import BoxList
+    g = torch.Generator().manual_seed(2468)
+    R = 24
+    logits = torch.randn(R, 9, 28, 28, generator=g) * 2
+    xy = torch.rand(R, 2, generator=g) * 400
+    wh = torch.rand(R, 2, generator=g) * 300 + 8
+    boxes = torch.cat([xy, xy + wh], 1)
+    out = {"logits": logits.numpy(), "boxes": boxes.numpy()}
+    torch.Tensor.get_device = lambda self: "cpu"
+    for stage in range(3):
+        pp = GridPostProcessor(stage, 9, 14)
+        bl = BoxList(boxes.clone(), (1000, 1000), mode="xyxy")
+        res = pp.get_boxes(bl, logits.clone(), False)
+        out["stage%d" % stage] = res.numpy()
+        out["sub_regions"] = np.asarray(pp.sub_regions, dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
+
+
+def main():
+    build_ref.build(cuda=False)
+    ref = build_ref.load("pet_ref_cpu")
+    install_shims(ref)
+    feats, rois = gen_roi_align(ref)
+    gen_pooler(feats, rois)
+    gen_levels()
+    gen_nms(ref)
+    gen_decode()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

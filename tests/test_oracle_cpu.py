@@ -1,0 +1,123 @@
+"""Pins the CPU oracle (oracle/cpm_oracle.c) against fixtures produced by the reference itself
+(tests/golden/make_golden.py) and against torchvision's CPU nms.  No GPU, no /root/reference needed."""
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+import oracle
+
+SCALES = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+CASES = [("p7s2", 7, 7, 2, False, [0, 1, 2, 3]), ("p14s2", 14, 14, 2, False, [0, 2]),
+         ("p7s0", 7, 7, 0, False, [1]), ("p7s2a", 7, 7, 2, True, [1, 3]), ("p5x3s3", 5, 3, 3, False, [2])]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_roi_align_matches_reference_bit_exact(golden, case):
+    g = golden("roi_align")
+    tag, ph, pw, sr, al, levels = case
+    rois = g["rois"][g[tag + "_sel"]]
+    for l in levels:
+        feat = g["feat%d" % l]
+        out = oracle.roi_align_forward(feat, rois, SCALES[l], ph, pw, sr, al)
+        assert np.array_equal(out, g["%s_l%d_out" % (tag, l)])
+        B, C, H, W = feat.shape
+        gin = oracle.roi_align_backward(g["%s_l%d_gout" % (tag, l)], rois, SCALES[l], ph, pw, B, C, H, W, sr, al)
+        assert np.array_equal(gin, g["%s_l%d_gin" % (tag, l)])
+
+
+def test_roi_align_aligned_negative_size_raises():
+    feat = np.zeros((1, 1, 8, 8), np.float32)
+    rois = np.array([[0, 5, 5, 2, 2]], np.float32)
+    with pytest.raises(RuntimeError):
+        oracle.roi_align_forward(feat, rois, 1.0, 2, 2, 2, True, strict_aligned_check=True)
+    # the CUDA reference has no such assert (ROIAlign_cuda.cu:211-214): default is non-strict
+    oracle.roi_align_forward(feat, rois, 1.0, 2, 2, 2, True)
+
+
+def test_roi_align_fp64_and_nearest_run():
+    rng = np.random.default_rng(0)
+    feat = rng.standard_normal((1, 2, 9, 11))
+    rois = np.array([[0, 1.5, 2.0, 30.0, 25.0], [0, -4, -4, 50, 50]])
+    o64 = oracle.roi_align_forward(feat, rois, 0.25, 4, 4, 2, False)
+    o32 = oracle.roi_align_forward(feat.astype(np.float32), rois.astype(np.float32), 0.25, 4, 4, 2, False)
+    assert o64.dtype == np.float64 and np.allclose(o64, o32, atol=1e-5)
+    near = oracle.roi_align_forward(feat, rois, 0.25, 4, 4, 2, False, interpolation_method=1)
+    assert near.shape == (2, 2, 4, 4) and np.isfinite(near).all()
+
+
+def test_pooler_composition_matches_reference(golden):
+    """levels (poolers.py:29-40) + per-level RoIAlign + scatter == the reference Pooler output."""
+    g, ra = golden("pooler"), golden("roi_align")
+    rois = ra["rois"][g["order"]]
+    levels = oracle.level_map(rois, 2, 5)
+    assert np.array_equal(levels, g["levels"])
+    feats = [ra["feat%d" % l] for l in range(4)]
+    for tag, p in (("p7", 7), ("p14", 14)):
+        out = np.zeros((len(rois), feats[0].shape[1], p, p), np.float32)
+        for l in range(4):
+            idx = np.nonzero(levels == l)[0]
+            out[idx] = oracle.roi_align_forward(feats[l], rois[idx], SCALES[l], p, p, 2, False)
+            B, C, H, W = feats[l].shape
+            gin = oracle.roi_align_backward(g[tag + "_gout"][idx], rois[idx], SCALES[l], p, p, B, C, H, W, 2, False)
+            assert np.array_equal(gin, g["%s_gin%d" % (tag, l)])
+        assert np.array_equal(out, g[tag + "_out"])
+
+
+def test_level_map_matches_reference(golden):
+    g = golden("levels")
+    rois = np.concatenate([np.zeros((len(g["boxes"]), 1), np.float32), g["boxes"]], 1)
+    assert np.array_equal(oracle.level_map(rois, 2, 5), g["levels"])
+    # torch's CUDA scalar division (a * (1/b)) gives the same levels on this set
+    assert np.array_equal(oracle.level_map(rois, 2, 5, recip_div=True), g["levels"])
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.7])
+def test_nms_matches_torchvision_and_reference_softnms(golden, thr):
+    g = golden("nms")
+    k = oracle.nms(g["boxes"], g["scores"], thr)
+    assert np.array_equal(k, g["nms_keep_%02d" % int(thr * 10)])
+    assert np.array_equal(np.sort(k), g["softnms_hard_keep_%02d" % int(thr * 10)])
+    km = oracle.nms(g["boxes"], g["scores"], thr, labels=g["labels"])
+    assert np.array_equal(km, g["mlnms_keep_%02d" % int(thr * 10)])
+    # topk: the sweep stops after topk keeps (ml_nms.cu:134)
+    assert np.array_equal(oracle.nms(g["boxes"], g["scores"], thr, labels=g["labels"], topk=17), km[:17])
+
+
+def test_nms_ties_and_degenerate(golden):
+    g = golden("nms")
+    assert np.array_equal(oracle.nms(g["boxes"], g["tie_scores"], 0.5), g["tie_keep_05"])
+    assert oracle.nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).size == 0
+    # two identical zero-area boxes: IoU = NaN, comparison false -> both kept
+    b = np.array([[3, 3, 3, 3], [3, 3, 3, 3]], np.float32)
+    assert oracle.nms(b, np.array([0.9, 0.8], np.float32), 0.5).tolist() == [0, 1]
+
+
+def test_nms_random_vs_torchvision_live():
+    gen = torch.Generator().manual_seed(5)
+    for n in (1, 2, 63, 64, 65, 1000):
+        xy = torch.rand(n, 2, generator=gen) * 300
+        wh = torch.rand(n, 2, generator=gen) * 120 + 1
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.rand(n, generator=gen)
+        for thr in (0.3, 0.7):
+            ref = torchvision.ops.nms(boxes, scores, thr).numpy()
+            assert np.array_equal(oracle.nms(boxes.numpy(), scores.numpy(), thr), ref)
+
+
+def test_nms_flavors_agree_away_from_threshold(golden):
+    """The three fp32 roundings of the union only differ for IoUs within an ulp of the threshold."""
+    g = golden("nms")
+    k0 = oracle.nms(g["boxes"], g["scores"], 0.5, flavor=oracle.FLAVOR_PLAIN)
+    k1 = oracle.nms(g["boxes"], g["scores"], 0.5, flavor=oracle.FLAVOR_TV_CUDA)
+    k2 = oracle.nms(g["boxes"], g["scores"], 0.5, flavor=oracle.FLAVOR_ML_CUDA)
+    assert np.array_equal(k0, k1) and np.array_equal(k0, k2)
+
+
+def test_decode_matches_reference(golden):
+    g = golden("decode")
+    sub = oracle.calc_sub_regions(9, 3, 56)
+    assert np.array_equal(np.asarray(sub, np.int32), g["sub_regions"])
+    for stage, ratio in enumerate((1.0, 0.5, 0.25)):
+        out = oracle.grid_decode(g["logits"], g["boxes"], sub, ratio)
+        np.testing.assert_allclose(out, g["stage%d" % stage], rtol=1e-5, atol=1e-3)
