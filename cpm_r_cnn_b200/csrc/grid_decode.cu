@@ -1,0 +1,137 @@
+// Grid-point heat-map -> box decode on the device.
+//
+// Replaces GridPostProcessor.get_boxes (pet/rcnn/modeling/grid_cascade_rcnn/inference.py:189-279), which copies the
+// whole (R, P, h, w) heat-map stack and the boxes to the host (:195-196), reduces there and copies the boxes back
+// (:278).  Here one CTA decodes one RoI: a warp per grid point streams that point's h*w logits with 16-byte loads,
+// keeps the running (sigmoid, first index) maximum per lane and finishes with a shuffle reduction; four threads then
+// form the score-weighted boundary votes (:251-271).  Traffic = the logits once (R*P*h*w*4 bytes) + 32 bytes per RoI.
+#include "common.cuh"
+
+namespace cpm {
+
+int check_device_ptr(const void* p, const char* what);
+
+constexpr int kMaxPoints = 64;
+
+struct SubXY {
+  int v[2 * kMaxPoints];
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void argmax_merge(float& bs, int& bi, float s, int i) {
+  // torch.max(dim): the first index among equal maxima (inference.py:204)
+  if (s > bs || (s == bs && i < bi)) {
+    bs = s;
+    bi = i;
+  }
+}
+
+__global__ void __launch_bounds__(256) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+                                                           int P, int gs, int h, int w, SubXY sub, float ratio,
+                                                           float* __restrict__ out_boxes, float* __restrict__ out_scores) {
+  __shared__ float sc[kMaxPoints], ax[kMaxPoints], ay[kMaxPoints];
+  const long r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int hw = h * w;
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + 4 * r);
+  const float width = bx.z - bx.x, height = bx.w - bx.y;
+  const float x1 = bx.x - ratio * (width / 2), y1 = bx.y - ratio * (height / 2);
+  for (int p = warp; p < P; p += nwarps) {
+    const float* m = logits + (r * P + p) * (long)hw;
+    float bs = -1.f;
+    int bi = 0x7fffffff;
+    if ((hw & 3) == 0) {
+      const float4* m4 = reinterpret_cast<const float4*>(m);
+      for (int i = lane; i < hw / 4; i += 32) {
+        const float4 v = __ldg(m4 + i);
+        argmax_merge(bs, bi, sigmoidf_ref(v.x), 4 * i + 0);
+        argmax_merge(bs, bi, sigmoidf_ref(v.y), 4 * i + 1);
+        argmax_merge(bs, bi, sigmoidf_ref(v.z), 4 * i + 2);
+        argmax_merge(bs, bi, sigmoidf_ref(v.w), 4 * i + 3);
+      }
+    } else {
+      for (int i = lane; i < hw; i += 32) argmax_merge(bs, bi, sigmoidf_ref(__ldg(m + i)), i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      argmax_merge(bs, bi, s2, i2);
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;   // all-NaN map
+      const int xs = bi % w + sub.v[2 * p], ys = bi / w + sub.v[2 * p + 1];
+      sc[p] = bs;
+      ax[p] = ((float)xs + 0.5f) / (float)(2 * w) * (1.f + ratio) * width + x1;      // inference.py:246
+      ay[p] = ((float)ys + 0.5f) / (float)(2 * h) * (1.f + ratio) * height + y1;     // inference.py:247
+      if (out_scores) out_scores[r * P + p] = bs;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    // boundary votes, inference.py:251-271: x1 <- points [0..gs), y1 <- [0, gs, 2gs, ..], x2 <- last gs, y2 <- [gs-1, 2gs-1, ..]
+    const int e = threadIdx.x;
+    float num = 0.f, den = 0.f;
+    for (int i = 0; i < gs; i++) {
+      const int idx = e == 0 ? i : e == 1 ? i * gs : e == 2 ? P - gs + i : (i + 1) * gs - 1;
+      const float a = (e & 1) ? ay[idx] : ax[idx];
+      num += a * sc[idx];
+      den += sc[idx];
+    }
+    out_boxes[4 * r + e] = num / den;
+  }
+}
+
+// LevelMapper alone (poolers.py:29-40)
+__global__ void level_map_kernel(const float* __restrict__ rois, long K, MapperView mp, long long* __restrict__ levels) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const float* r = rois + 5 * i;
+  levels[i] = fpn_level(r[1], r[2], r[3], r[4], mp);
+}
+
+}  // namespace cpm
+
+using namespace cpm;
+
+extern "C" int cpm_grid_decode(const float* d_logits, const float* d_boxes, int64_t R, int P, int h, int w,
+                               const int32_t* sub_xy, float mapping_ratio, float* d_out_boxes, float* d_out_scores,
+                               void* stream) {
+  CPM_CHECK_ARG(R >= 0 && R < (1LL << 31), "R out of range");
+  CPM_CHECK_ARG(P >= 1 && P <= kMaxPoints, "P must be in [1,%d]", kMaxPoints);
+  int gs = 1;
+  while (gs * gs < P) gs++;
+  CPM_CHECK_ARG(gs * gs == P, "P must be a square number (grid_size^2)");
+  CPM_CHECK_ARG(h >= 1 && w >= 1, "empty heat-map");
+  CPM_CHECK_ARG(sub_xy != nullptr, "sub_xy is NULL");
+  if (R == 0) return CPM_OK;
+  int rc;
+  if ((rc = check_device_ptr(d_logits, "logits")) != CPM_OK) return rc;
+  if ((rc = check_device_ptr(d_boxes, "boxes")) != CPM_OK) return rc;
+  if ((rc = check_device_ptr(d_out_boxes, "out_boxes")) != CPM_OK) return rc;
+  CPM_CHECK_ARG(((uintptr_t)d_boxes & 15) == 0 && ((uintptr_t)d_logits & 15) == 0, "logits/boxes must be 16-byte aligned");
+  SubXY sub;
+  for (int i = 0; i < 2 * P; i++) sub.v[i] = sub_xy[i];
+  for (int i = 2 * P; i < 2 * kMaxPoints; i++) sub.v[i] = 0;
+  int warps = P < 8 ? P : 8;
+  if (P == 9) warps = 9;
+  grid_decode_kernel<<<(unsigned)R, 32 * warps, 0, (cudaStream_t)stream>>>(d_logits, d_boxes, P, gs, h, w, sub,
+                                                                          mapping_ratio, d_out_boxes, d_out_scores);
+  CPM_CHECK_LAUNCH();
+  return CPM_OK;
+}
+
+extern "C" int cpm_level_map(const float* d_rois, int64_t K, const cpm_level_mapper_t* mapper, int64_t* d_levels,
+                             void* stream) {
+  CPM_CHECK_ARG(K >= 0, "K < 0");
+  CPM_CHECK_ARG(mapper != nullptr, "mapper is NULL");
+  if (K == 0) return CPM_OK;
+  int rc;
+  if ((rc = check_device_ptr(d_rois, "rois")) != CPM_OK) return rc;
+  if ((rc = check_device_ptr(d_levels, "levels")) != CPM_OK) return rc;
+  level_map_kernel<<<(unsigned)((K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_rois, K, make_view(mapper),
+                                                                                (long long*)d_levels);
+  CPM_CHECK_LAUNCH();
+  return CPM_OK;
+}

@@ -1,0 +1,113 @@
+"""LevelMapper + Pooler with the reference's interface (pet/rcnn/utils/poolers.py:9-40, :43-132).
+
+The reference walks the FPN levels in Python: nonzero() (host sync) -> gather rois -> ROIAlign -> index_put, once per
+level (poolers.py:127-130).  Here the whole pyramid is ONE kernel launch: the FPN level of every RoI (Eqn. 1 of the FPN
+paper, poolers.py:35-40) is evaluated inside the RoIAlign kernel and each RoI's block lands at its own row of the
+output; the backward is one launch that produces the dense gradient of every level.
+"""
+import ctypes
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+from .roi_align import INTERPOLATION_METHOD, ROIAlign, _float_function, pooler_backward, pooler_forward
+
+
+class LevelMapper(object):
+    """poolers.py:9-40.  __call__(boxlists) -> int64 level index per box, computed on the device."""
+
+    def __init__(self, k_min, k_max, canonical_scale=224, canonical_level=4, eps=1e-6):
+        self.k_min = k_min
+        self.k_max = k_max
+        self.s0 = canonical_scale
+        self.lvl0 = canonical_level
+        self.eps = eps
+
+    def c_struct(self):
+        return _lib.make_mapper(self.k_min, self.k_max, self.s0, self.lvl0, self.eps)
+
+    def __call__(self, boxlists):
+        boxes = torch.cat([b.bbox for b in boxlists], dim=0)
+        return self.map_boxes(boxes)
+
+    def map_boxes(self, boxes):
+        """(K,4) xyxy boxes -> (K,) int64 levels (area with the +1 convention, bounding_box.py:306-310)."""
+        _lib.require_cuda(boxes, "boxes")
+        K = boxes.shape[0]
+        rois = torch.cat([boxes.new_zeros((K, 1)), boxes.float()], dim=1).contiguous()
+        out = torch.empty((K,), dtype=torch.int64, device=boxes.device)
+        if K:
+            m = self.c_struct()
+            with _lib.device_of(rois):
+                _lib.check(_lib.lib().cpm_level_map(_lib.ptr(rois), K, ctypes.byref(m), _lib.ptr(out),
+                                                    _lib.stream_ptr(boxes.device)))
+        return out
+
+
+class _PyramidROIAlign(Function):
+    """Multi-level RoIAlign as one autograd node: forward(rois, cfg, *levels) -> (K,C,PH,PW)."""
+
+    @staticmethod
+    def forward(ctx, rois, cfg, *levels):
+        ctx.save_for_backward(rois)
+        ctx.cfg = cfg
+        ctx.shapes = [tuple(t.shape) for t in levels]
+        output_size, scales, sampling_ratio, aligned, interp, mapper = cfg
+        return pooler_forward(list(levels), scales, rois, output_size, sampling_ratio, aligned, interp, mapper)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        rois, = ctx.saved_tensors
+        output_size, scales, sampling_ratio, aligned, interp, mapper = ctx.cfg
+        grads = pooler_backward(grad_output, ctx.shapes, scales, rois, output_size, sampling_ratio, aligned, interp,
+                                mapper)
+        return (None, None) + tuple(grads)
+
+
+class Pooler(nn.Module):
+    """poolers.py:43-132: Pooler(method, output_size, scales, sampling_ratio, rotated=False, interpolation)."""
+
+    def __init__(self, method, output_size, scales, sampling_ratio, rotated=False, interpolation="bilinear"):
+        assert method in {'ROIPool', 'ROIAlign', 'ROIAlignV2', 'ROIAlignRotated'}, \
+            'Unknown pooling method: {}'.format(method)
+        if method in ('ROIPool', 'ROIAlignRotated') or rotated:
+            # out of the hot path: no CPM config selects them (config.py:877)
+            raise NotImplementedError("cpm_ops implements the ROIAlign / ROIAlignV2 poolers only")
+        super(Pooler, self).__init__()
+        self.output_size = _pair(output_size)
+        self.scales = [float(s) for s in scales]
+        self.sampling_ratio = sampling_ratio
+        self.aligned = "V2" in method
+        self.interpolation = interpolation
+        self.poolers = nn.ModuleList([
+            ROIAlign(self.output_size, spatial_scale=s, sampling_ratio=sampling_ratio, aligned=self.aligned,
+                     interpolation=interpolation) for s in scales])
+        lvl_min = -torch.log2(torch.tensor(scales[0], dtype=torch.float32)).item()
+        lvl_max = -torch.log2(torch.tensor(scales[-1], dtype=torch.float32)).item()
+        self.map_levels = LevelMapper(lvl_min, lvl_max)
+
+    def convert_to_roi_format(self, boxes):
+        """poolers.py:90-101: (K,5) [image index, x1, y1, x2, y2] in the boxes' dtype."""
+        concat_boxes = torch.cat([b.bbox for b in boxes], dim=0)
+        counts = torch.tensor([len(b) for b in boxes], dtype=torch.int64)
+        ids = torch.repeat_interleave(torch.arange(len(boxes), dtype=concat_boxes.dtype), counts)
+        ids = ids.to(concat_boxes.device, non_blocking=True)
+        return torch.cat([ids[:, None], concat_boxes], dim=1)
+
+    def forward(self, x, boxes):
+        """x: list[Tensor] feature maps (one per level, extra levels are ignored like zip() does at poolers.py:127);
+        boxes: list[BoxList].  Returns (K, C, PH, PW) in x[0].dtype."""
+        num_levels = len(self.poolers)
+        rois = self.convert_to_roi_format(boxes)
+        if num_levels == 1:
+            return self.poolers[0](x[0], rois)
+        levels = [_float_function(t) for t in list(x)[:num_levels]]
+        rois = _float_function(rois).to(levels[0].dtype)
+        cfg = (self.output_size, self.scales[:len(levels)], self.sampling_ratio, self.aligned,
+               INTERPOLATION_METHOD[self.interpolation], self.map_levels.c_struct())
+        return _PyramidROIAlign.apply(rois, cfg, *levels)

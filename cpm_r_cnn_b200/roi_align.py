@@ -1,0 +1,183 @@
+"""RoIAlign op layer: same names and signatures as the reference's pet/lib/ops/roi_align.py
+(_ROIAlign :14-60, roi_align :63, ROIAlign :66-95), bound to libcpm_ops.so instead of pet.lib.ops._C.
+
+Layout: the hot kernels read NHWC.  A torch.channels_last (B,C,H,W) tensor is passed through zero-copy; an
+NCHW-contiguous fp32 map is staged once per call with cpm_layout_convert (pure streaming; see stage_nhwc to do it
+once for several poolers); fp64 / nearest interpolation use the reference-shaped generic kernel on NCHW directly.
+The dense input gradient is produced in NHWC and returned as a channels_last-strided (B,C,H,W) tensor.
+"""
+import ctypes
+import os
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+
+INTERPOLATION_METHOD = {"bilinear": 0, "nearest": 1}
+
+# "deterministic" (atomic-free tile-owner gather) or "atomic" (red.global.add scatter, the reference's semantics)
+BACKWARD_MODE = os.environ.get("CPM_ROI_ALIGN_BACKWARD", "deterministic")
+
+
+def _is_nhwc(t):
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def stage_nhwc(x):
+    """(B,C,H,W) any strides -> the same values as a channels_last tensor (zero-copy when it already is)."""
+    _lib.require_cuda(x, "input")
+    if _is_nhwc(x):
+        return x
+    if x.dtype not in _lib.DTYPES:
+        return x.contiguous(memory_format=torch.channels_last)
+    src = x.contiguous()
+    B, C, H, W = src.shape
+    dst = torch.empty((B, C, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with _lib.device_of(src):
+        _lib.check(_lib.lib().cpm_layout_convert(_lib.ptr(src), _lib.ptr(dst), B, C, H, W, _lib.DTYPES[x.dtype],
+                                                 _lib.NHWC, _lib.stream_ptr(x.device)))
+    return dst
+
+
+def make_pyramid(levels, scales, layout):
+    p = _lib.Pyramid()
+    B, C = levels[0].shape[0], levels[0].shape[1]
+    p.num_levels, p.batch, p.channels = len(levels), B, C
+    p.dtype, p.layout = _lib.DTYPES[levels[0].dtype], layout
+    for i, (t, s) in enumerate(zip(levels, scales)):
+        assert t.shape[0] == B and t.shape[1] == C and t.dtype == levels[0].dtype and t.device == levels[0].device
+        p.d_level[i] = t.data_ptr()
+        p.height[i], p.width[i] = t.shape[2], t.shape[3]
+        p.spatial_scale[i] = float(s)
+    return p
+
+
+def _prepare_levels(levels, interpolation):
+    """-> (tensors kept alive, layout).  fp32 bilinear goes to NHWC (staging NCHW inputs); the rest stays NCHW."""
+    dt = levels[0].dtype
+    if dt == torch.float32 and interpolation == 0 and levels[0].shape[1] % 4 == 0:
+        return [stage_nhwc(t) for t in levels], _lib.NHWC
+    return [t.contiguous() for t in levels], _lib.NCHW
+
+
+def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper, impl=_lib.FWD_AUTO):
+    """One launch for the whole pyramid: list[(B,C,H_l,W_l)] + (K,5) rois -> (K,C,PH,PW)."""
+    for t in levels:
+        _lib.require_cuda(t, "input")
+    _lib.require_cuda(rois, "rois")
+    x0 = levels[0]
+    if rois.dtype != x0.dtype or rois.device != x0.device:
+        # at::checkAllSameGPU / checkAllSameType, ROIAlign_cuda.cu:381-382
+        raise RuntimeError("cpm_ops: input and rois must have the same dtype and device (got %s/%s, %s/%s)"
+                           % (x0.dtype, x0.device, rois.dtype, rois.device))
+    if x0.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("cpm_ops: roi_align supports float32 and float64 inputs (got %s)" % x0.dtype)
+    ph, pw = output_size
+    K, C = rois.shape[0], x0.shape[1]
+    out = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device)
+    if K == 0:
+        return out
+    staged, layout = _prepare_levels(levels, interpolation)
+    pyr = make_pyramid(staged, scales, layout)
+    rois = rois.contiguous()
+    with _lib.device_of(x0):
+        _lib.check(_lib.lib().cpm_roi_align_forward(ctypes.byref(pyr), _lib.ptr(rois), K, ph, pw, int(sampling_ratio),
+                                                    int(bool(aligned)), interpolation,
+                                                    ctypes.byref(mapper) if mapper is not None else None, None, impl,
+                                                    _lib.ptr(out), _lib.stream_ptr(x0.device)))
+    return out
+
+
+def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper,
+                    mode=None):
+    """Dense gradients of every level: list[(B,C,H_l,W_l)] (channels_last strides on the NHWC path)."""
+    _lib.require_cuda(grad_output, "grad_output")
+    mode = BACKWARD_MODE if mode is None else mode
+    ph, pw = output_size
+    K = rois.shape[0]
+    dt, dev = grad_output.dtype, grad_output.device
+    B, C = shapes[0][0], shapes[0][1]
+    nhwc = dt == torch.float32 and interpolation == 0 and C % 4 == 0
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    grads = [torch.empty(tuple(s), dtype=dt, device=dev, memory_format=fmt) for s in shapes]
+    if B == 0 or any(g.numel() == 0 for g in grads):
+        return grads
+    pyr = make_pyramid(grads, scales, _lib.NHWC if nhwc else _lib.NCHW)
+    grad_output = grad_output.contiguous()
+    rois = rois.contiguous()
+    det_ok = nhwc and sampling_ratio >= 1 and ph <= 32 and pw <= 32
+    use = _lib.BWD_DETERMINISTIC if (mode == "deterministic" and det_ok) else _lib.BWD_ATOMIC
+    ws, ws_bytes = None, 0
+    with _lib.device_of(grad_output):
+        if use == _lib.BWD_DETERMINISTIC:
+            ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes(K, len(shapes), B))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().cpm_roi_align_backward(ctypes.byref(pyr), _lib.ptr(grad_output), _lib.ptr(rois), K, ph, pw,
+                                                     int(sampling_ratio), int(bool(aligned)), interpolation,
+                                                     ctypes.byref(mapper) if mapper is not None else None, None, use,
+                                                     _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+    return grads
+
+
+class _ROIAlign(Function):
+    """pet/lib/ops/roi_align.py:14-60 (same argument list, same `(grad_input, None x 6)` backward)."""
+
+    @staticmethod
+    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio, aligned, interpolation="bilinear"):
+        ctx.save_for_backward(roi)
+        ctx.output_size = _pair(output_size)
+        ctx.spatial_scale = spatial_scale
+        ctx.sampling_ratio = sampling_ratio
+        ctx.input_shape = input.size()
+        ctx.aligned = aligned
+        ctx.interpolation_method = INTERPOLATION_METHOD[interpolation]
+        return pooler_forward([input], [spatial_scale], roi, ctx.output_size, sampling_ratio, aligned,
+                              ctx.interpolation_method, None)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        rois, = ctx.saved_tensors
+        grad_input = pooler_backward(grad_output, [ctx.input_shape], [ctx.spatial_scale], rois, ctx.output_size,
+                                     ctx.sampling_ratio, ctx.aligned, ctx.interpolation_method, None)[0]
+        return grad_input, None, None, None, None, None, None
+
+
+roi_align = _ROIAlign.apply
+
+
+def _float_function(x):
+    """apex.amp.float_function (roi_align.py:76): half inputs are computed in fp32."""
+    return x.float() if x.dtype in (torch.float16, torch.bfloat16) else x
+
+
+class ROIAlign(nn.Module):
+    """pet/lib/ops/roi_align.py:66-95."""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio, aligned, interpolation="bilinear"):
+        assert interpolation in INTERPOLATION_METHOD, "Unknown interpolation method: {}".format(interpolation)
+        super(ROIAlign, self).__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+        self.aligned = aligned
+        self.interpolation_method = interpolation
+
+    def forward(self, input, rois):
+        """input: NCHW images (any strides); rois: Bx5 boxes, first column = index into N, then xyxy."""
+        assert rois.dim() == 2 and rois.size(1) == 5
+        return roi_align(_float_function(input), _float_function(rois), self.output_size, self.spatial_scale,
+                         self.sampling_ratio, self.aligned, self.interpolation_method)
+
+    def __repr__(self):
+        tmpstr = self.__class__.__name__ + "("
+        tmpstr += "output_size=" + str(self.output_size)
+        tmpstr += ", spatial_scale=" + str(self.spatial_scale)
+        tmpstr += ", sampling_ratio=" + str(self.sampling_ratio)
+        tmpstr += ", aligned=" + str(self.aligned)
+        tmpstr += ")"
+        return tmpstr

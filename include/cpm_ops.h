@@ -1,0 +1,180 @@
+/*
+ * cpm_ops.h -- C ABI of the B200-native (sm_100a) CPM R-CNN detection-head op library (libcpm_ops.so).
+ *
+ * This is the drop-in boundary for the reference's native extension `pet.lib.ops._C`
+ * (pybind module, /root/reference/pet/lib/ops/csrc/vision.cpp:21-22,32).  Each entry point cites the
+ * reference interface it replaces.  Conventions:
+ *   - plain pointers and sizes only; no torch / ATen types;
+ *   - every pointer named `d_*` is a DEVICE pointer on the current CUDA device; the caller owns all
+ *     memory (outputs and workspaces are allocated by the caller, e.g. with torch's caching allocator);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises
+ *     the device (the reference does: ROIAlign_cuda.cu:422, ml_nms.cu:117);
+ *   - return value: CPM_OK (0) or a negative CPM_ERR_* code; cpm_last_error() gives the message
+ *     (thread-local).  The reference signals the same conditions with C++ exceptions
+ *     (AT_ASSERTM / AT_ERROR -> Python RuntimeError); the Python host layer re-raises as RuntimeError;
+ *   - there is no CPU fallback: a NULL/host pointer is an error, not a slow path.
+ */
+#ifndef CPM_OPS_H_
+#define CPM_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CPM_API __attribute__((visibility("default")))
+#else
+#define CPM_API
+#endif
+
+#define CPM_OK 0
+#define CPM_ERR_INVALID_ARG (-1)
+#define CPM_ERR_UNSUPPORTED (-2)
+#define CPM_ERR_WORKSPACE (-3)
+#define CPM_ERR_CUDA (-4)
+
+#define CPM_MAX_LEVELS 8
+
+/* element types of feature maps / pooled outputs / gradients */
+#define CPM_F32 0
+#define CPM_F64 1   /* the reference dispatches float and double on the GPU (ROIAlign_cuda.cu:406) */
+#define CPM_BF16 2  /* new on this path: bf16 storage, fp32 accumulation (NHWC kernels only) */
+
+/* memory layout of one feature-map level */
+#define CPM_LAYOUT_NCHW 0   /* (B, C, H, W) contiguous: what the reference's kernels index (ROIAlign_cuda.cu:219) */
+#define CPM_LAYOUT_NHWC 1   /* (B, H, W, C) contiguous == a torch.channels_last (B,C,H,W) tensor; the fast kernels' layout */
+
+/* interpolation_method of ROIAlign.h:57-65 (pet/lib/ops/roi_align.py:11) */
+#define CPM_INTERP_BILINEAR 0
+#define CPM_INTERP_NEAREST 1
+
+/* how the fp32 union `Sa + Sb - inter` of the IoU is rounded (see oracle/cpm_oracle.c: orc_nms) */
+#define CPM_IOU_PLAIN 0      /* every op rounded separately (source-level semantics, torchvision CPU)        */
+#define CPM_IOU_TV_CUDA 1    /* fmaf(bw,bh,Sa) - inter : what torchvision 0.26's sm_100 nms kernel executes   */
+#define CPM_IOU_ML_CUDA 2    /* fmaf(aw,ah,Sb) - inter : what nvcc 12.9 makes of the reference ml_nms.cu:23-25 */
+
+/* backward accumulation mode */
+#define CPM_BWD_DETERMINISTIC 0   /* atomic-free: pixel tiles own their gradient, fixed summation order */
+#define CPM_BWD_ATOMIC 1          /* red.global.add.f32 scatter (non-deterministic order; reported separately) */
+
+/* forward implementation selector (testing / benchmarking aid; AUTO is what callers use) */
+#define CPM_FWD_AUTO 0
+#define CPM_FWD_GENERIC 1         /* one thread per output element, any parameters / layout, fp32/fp64 */
+#define CPM_FWD_NHWC 2            /* warp-per-bin-row channel-vector gather (bilinear, NHWC, fp32/bf16, C % 4 == 0) */
+
+/*
+ * A feature pyramid (or the pyramid of dense feature gradients): L levels of dense maps that share batch
+ * size B, channel count C, element type and layout.  Replaces the list[Tensor] the reference's Pooler walks
+ * (pet/rcnn/utils/poolers.py:103-132) and, with L == 1, the single `input` of
+ * _C.roi_align_forward (ROIAlign.h:57-65).
+ */
+typedef struct cpm_pyramid {
+  int32_t num_levels;                 /* L in [1, CPM_MAX_LEVELS] */
+  int32_t batch;                      /* B */
+  int32_t channels;                   /* C */
+  int32_t dtype;                      /* CPM_F32 | CPM_F64 | CPM_BF16 */
+  int32_t layout;                     /* CPM_LAYOUT_NCHW | CPM_LAYOUT_NHWC (all levels) */
+  int32_t reserved;
+  void* d_level[CPM_MAX_LEVELS];      /* level l: B*C*H_l*W_l elements, dense, in `layout` order */
+  int32_t height[CPM_MAX_LEVELS];
+  int32_t width[CPM_MAX_LEVELS];
+  float spatial_scale[CPM_MAX_LEVELS];
+} cpm_pyramid_t;
+
+/*
+ * FPN level heuristic, LevelMapper (poolers.py:9-40):
+ *   lvl = clamp(floor(lvl0 + log2(sqrt(area) / s0 + eps)), k_min, k_max) - k_min,
+ *   area = (x2 - x1 + 1) * (y2 - y1 + 1)                      (bounding_box.py:306-310).
+ * Fused into the RoIAlign kernels when num_levels > 1.  `s / s0` is evaluated as s * (1 / s0), which is
+ * how torch evaluates tensor / python-scalar on CUDA (the device the reference runs on).
+ */
+typedef struct cpm_level_mapper {
+  float k_min, k_max;                 /* -log2(scales[0]), -log2(scales[-1])  (poolers.py:86-88) */
+  float canonical_scale;              /* 224 */
+  float canonical_level;              /* 4 */
+  float eps;                          /* 1e-6 */
+} cpm_level_mapper_t;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+CPM_API const char* cpm_last_error(void);
+CPM_API int cpm_version(void);
+/* number of kernels this library has launched in this process (monotonic; bench.py's gpu_launches) */
+CPM_API uint64_t cpm_launch_count(void);
+/* binds the calling thread to CUDA device `device` for subsequent calls (CUDAGuard of ROIAlign_cuda.cu:383) */
+CPM_API int cpm_set_device(int device);
+
+/* ---- RoIAlign -------------------------------------------------------------------------------------
+ * Forward.  Replaces _C.roi_align_forward (ROIAlign.h:57-96 -> ROIAlign_cuda.cu:367-425, kernel :178-256)
+ * and, for num_levels > 1, the whole per-level loop of Pooler.forward (poolers.py:117-131): every RoI is
+ * pooled from the level the mapper assigns it, results land at the RoI's own row of `d_out`
+ * (K, C, PH, PW) -- one launch, no nonzero()/index_put, no device sync.
+ *   d_rois      (K,5) [batch_idx, x1, y1, x2, y2], same dtype as the pyramid (ROIAlign_cuda.cu:381-382)
+ *   mapper      ignored when num_levels == 1; d_roi_levels (optional, int32[K]) overrides the mapper
+ *   impl        CPM_FWD_AUTO | CPM_FWD_GENERIC | CPM_FWD_SEPARABLE
+ * K == 0 is a no-op (ROIAlign_cuda.cu:401-404). */
+CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
+                          int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,
+                          const int32_t* d_roi_levels, int impl, void* d_out, void* stream);
+
+/* Backward.  Replaces _C.roi_align_backward (ROIAlign.h:98-146 -> ROIAlign_cuda.cu:428-487, kernel :259-365).
+ * `grad_feat` describes the OUTPUT maps: every level is fully written (dense gradient, zeros where no RoI
+ * reaches -- the reference's at::zeros + atomicAdd, :451-452,:340-347), also when K == 0.
+ *   mode        CPM_BWD_DETERMINISTIC (needs the workspace) | CPM_BWD_ATOMIC
+ * Workspace: cpm_roi_align_backward_workspace_bytes(K, num_levels) bytes, 256-byte aligned. */
+CPM_API size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch);
+CPM_API int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
+                           int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
+                           const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* LevelMapper alone (poolers.py:29-40): d_levels int64[K]. */
+CPM_API int cpm_level_map(const float* d_rois, int64_t K, const cpm_level_mapper_t* mapper, int64_t* d_levels, void* stream);
+
+/* ---- layout staging --------------------------------------------------------------------------------
+ * One level (B, C, H, W) <-> (B, H, W, C).  `to_layout` is the layout of d_dst; d_src is in the other one.
+ * The fast RoIAlign kernels read/write NHWC; torch.channels_last tensors need no staging at all. */
+CPM_API int cpm_layout_convert(const void* d_src, void* d_dst, int batch, int channels, int height, int width, int dtype,
+                       int to_layout, void* stream);
+
+/* ---- NMS ------------------------------------------------------------------------------------------
+ * Hard NMS over N boxes (x1,y1,x2,y2), fp32.  Replaces
+ *   d_labels == NULL : pet.lib.ops.nms = torchvision.ops.nms (pet/lib/ops/nms.py:2,10)
+ *   d_labels != NULL : _C.ml_nms (ml_nms.h:16-39 -> ml_nms.cu:82-146): a pair is only compared when labels match.
+ * Sort (stable, descending score), IoU bitmask and suppression sweep all run on the device.
+ *   d_keep   int64[N]  indices into the input, descending score (ml_nms.cu:143-145); first *d_count are valid
+ *   d_count  int64[1]  number kept; `topk` > 0 stops the sweep after topk keeps (ml_nms.cu:134)
+ * N == 0 writes *d_count = 0. */
+CPM_API size_t cpm_nms_workspace_bytes(int64_t N);
+CPM_API int cpm_nms(const float* d_boxes, const float* d_scores, const int64_t* d_labels, int64_t N, float iou_threshold,
+            int64_t topk, int iou_flavor, int64_t* d_keep, int64_t* d_count, void* d_workspace,
+            size_t workspace_bytes, void* stream);
+
+/* Batched NMS: independent segments (image x class, or image x FPN level) in ONE call -- the per-image /
+ * per-level Python loops of rpn/inference.py:102-113 and grid_cascade_rcnn/inference.py:91-97.
+ *   d_segments int32[N] segment id of each box in [0, num_segments)
+ *   d_keep     int64[N] kept indices grouped by segment (ascending id), descending score inside a segment
+ *   d_seg_counts int64[num_segments] kept per segment (after topk_per_segment, 0 = unlimited)
+ *   d_count    int64[1] total kept */
+CPM_API size_t cpm_nms_batched_workspace_bytes(int64_t N, int64_t num_segments);
+CPM_API int cpm_nms_batched(const float* d_boxes, const float* d_scores, const int32_t* d_segments, int64_t N,
+                    int64_t num_segments, float iou_threshold, int64_t topk_per_segment, int iou_flavor,
+                    int64_t* d_keep, int64_t* d_seg_counts, int64_t* d_count, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---- grid-point decode ------------------------------------------------------------------------------
+ * Replaces GridPostProcessor.get_boxes (grid_cascade_rcnn/inference.py:189-279), which moves the heat-maps
+ * to the host.  d_logits (R,P,h,w) fp32 PRE-sigmoid; d_boxes (R,4); sub_xy = HOST int32[P*2] (sub_x1, sub_y1)
+ * of calc_sub_regions (grid_rcnn/loss.py:244-273); P must be a square number <= 64.
+ *   d_out_boxes (R,4) un-clamped (the reference's clamp_ at :275-276 is a no-op)
+ *   d_out_scores (R,P) max sigmoid per point, may be NULL */
+CPM_API int cpm_grid_decode(const float* d_logits, const float* d_boxes, int64_t R, int P, int h, int w,
+                    const int32_t* sub_xy, float mapping_ratio, float* d_out_boxes, float* d_out_scores,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPM_OPS_H_ */
