@@ -27,7 +27,7 @@ __device__ __forceinline__ void argmax_merge(float& bs, int& bi, float s, int i)
   }
 }
 
-__global__ void __launch_bounds__(256) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+__global__ void __launch_bounds__(288) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                                            int P, int gs, int h, int w, SubXY sub, float ratio,
                                                            float* __restrict__ out_boxes, float* __restrict__ out_scores) {
   __shared__ float sc[kMaxPoints], ax[kMaxPoints], ay[kMaxPoints];

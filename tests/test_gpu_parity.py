@@ -52,9 +52,18 @@ def test_roi_align_golden_generic(golden, case):
         for dt in (torch.float32, torch.float64):
             feat = cuda(g["feat%d" % l], dt).requires_grad_(True)
             out = ops.roi_align(feat, cuda(rois, dt), (ph, pw), SCALES[l], sr, al)
-            close(out.detach().cpu(), g["%s_l%d_out" % (tag, l)], 1e-5 if dt == torch.float32 else 1e-12)
-            out.backward(cuda(g["%s_l%d_gout" % (tag, l)], dt))
-            close(feat.grad.cpu(), g["%s_l%d_gin" % (tag, l)], 1e-5 if dt == torch.float32 else 1e-12)
+            gout = g["%s_l%d_gout" % (tag, l)]
+            if dt == torch.float32:      # the reference's own fp32 outputs
+                ref, gref, rel = g["%s_l%d_out" % (tag, l)], g["%s_l%d_gin" % (tag, l)], 1e-5
+            else:                        # fp64 (dispatched by the reference on the GPU only): the oracle in double
+                f64, r64 = g["feat%d" % l].astype(np.float64), rois.astype(np.float64)
+                B, C, H, W = f64.shape
+                ref = oracle.roi_align_forward(f64, r64, SCALES[l], ph, pw, sr, al)
+                gref = oracle.roi_align_backward(gout.astype(np.float64), r64, SCALES[l], ph, pw, B, C, H, W, sr, al)
+                rel = 1e-12
+            close(out.detach().cpu(), ref, rel)
+            out.backward(cuda(gout, dt))
+            close(feat.grad.cpu(), gref, rel)
 
 
 def _random_case(seed, B, C, K, img=(200, 336), s_max=700.0):

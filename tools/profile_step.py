@@ -1,0 +1,43 @@
+"""One warm-up-then-measure pass of the bench step (7x7 + 14x14 Pooler fwd+bwd on the configs[1] workload) for ncu.
+    python tools/profile_step.py [--steps N] [--nms]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from cpm_r_cnn_b200 import _lib, synthetic as sy  # noqa: E402
+from cpm_r_cnn_b200.roi_align import pooler_backward, pooler_forward  # noqa: E402
+import cpm_r_cnn_b200 as ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--nms", action="store_true")
+ap.add_argument("--mode", default="deterministic")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+rois_h, feats_h, gouts_h = bench.make_workload(0)
+feats = [f.to(dev).contiguous(memory_format=torch.channels_last) for f in feats_h]
+rois = rois_h.to(dev)
+gouts = [g.to(dev) for g in gouts_h]
+shapes = [tuple(f.shape) for f in feats_h]
+mapper = _lib.make_mapper(2, 5)
+for i in range(args.steps):
+    for p, go in zip(bench.POOLERS, gouts):
+        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper)
+        grads = pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode)
+    torch.cuda.synchronize()
+if args.nms:
+    gen = torch.Generator().manual_seed(1000)
+    b, s, seg = sy.rpn_like_candidates(gen, 16, 5, 1000)
+    for i in range(2):
+        ops.batched_nms(b.to(dev), s.to(dev), seg.to(dev), 80, 0.7, sync=False)
+    b, s, seg, lab, img = sy.detection_candidates(gen, 16, 1000, 80, -1.0)
+    for i in range(2):
+        ops.batched_nms(b.to(dev), s.to(dev), seg.to(dev), 1280, 0.3, sync=False)
+    torch.cuda.synchronize()
+print("ok")
