@@ -40,7 +40,8 @@ _SIGNATURES = {
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p]),
-    "cpm_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "cpm_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "cpm_roi_align_backward": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int,

@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_red(PyramidView pv, co
 constexpr int TH = 8, TW = 8;          // tile: 8 rows (one per warp) x 8 columns (register-unrolled)
 constexpr int kTileThreads = 256;
 constexpr int kMaxP = 32;              // pooled size limit of this path (bin ranges are 32-bit ballots)
-constexpr int kStageBins = 32;         // bins of grad_out staged per round
 
 struct TileGrid {
   int tiles_x[CPM_MAX_LEVELS], tiles_y[CPM_MAX_LEVELS];
@@ -215,28 +214,114 @@ __global__ void __launch_bounds__(256) bwd_bin_rois(PyramidView pv, const float*
   }
 }
 
-struct Cand {
-  int roi;
-  float start_w, start_h, bin_w, bin_h;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+
+struct __align__(16) TapS {
+  int lo, hi;       // lo < 0: sample out of range
+  float wlo, whi;   // (1 - l), l   (bilinear_interpolate_gradient, ROIAlign_cuda.cu:155-160, per axis)
 };
 
-// swizzled staging row: bin e, channel c (of the chunk) -> word index; conflict-free both for the (8 bins x 4 channels)
-// patch stores and for the one-float4-per-lane row loads
-__device__ __forceinline__ int sgo_off(int e, int c) { return e * kChunk + ((((c >> 2) ^ (e & 7))) << 2) + (c & 3); }
+// One CTA per RoI: the RoI's sample taps along both axes (PH*G + PW*G entries) and the pixel box they reach.
+// taps layout: [K][(PH + PW) * G]  (y taps first); box: [K] int4 {ylo, yhi, xlo, xhi}, ylo > yhi when nothing is reached.
+__global__ void __launch_bounds__(64) bwd_roi_taps(PyramidView pv, const float* __restrict__ rois, int K, int PH, int PW, int G,
+                                                    int aligned, MapperView mp, const int* __restrict__ roi_levels,
+                                                    TapS* __restrict__ taps, int4* __restrict__ box) {
+  const int r = blockIdx.x;
+  const float* roi = rois + 5 * (long)r;
+  const int l = roi_level_b(roi, pv, mp, roi_levels, r);
+  const int nt = (PH + PW) * G;
+  TapS* out = taps + (long)r * nt;
+  const bool ok = l >= 0 && l < pv.num_levels && (int)roi[0] >= 0 && (int)roi[0] < pv.batch;
+  if (!ok) {
+    if (threadIdx.x == 0) box[r] = make_int4(1, 0, 1, 0);
+    return;
+  }
+  const int H = pv.H[l], W = pv.W[l];
+  const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
+  for (int e = threadIdx.x; e < nt; e += blockDim.x) {
+    const bool isy = e < PH * G;
+    const int k = isy ? e : e - PH * G;
+    const int p = k / G, i = k - p * G;
+    const float start = isy ? g.start_h : g.start_w, bin = isy ? g.bin_h : g.bin_w;
+    const float v = start + p * bin + static_cast<float>(i + .5f) * bin / static_cast<float>(G);
+    const AxisTap t = axis_tap(v, isy ? H : W);
+    TapS o;
+    o.lo = t.valid ? t.lo : -1;
+    o.hi = t.valid ? t.hi : -1;
+    o.wlo = t.wlo;
+    o.whi = t.whi;
+    out[e] = o;
+  }
+  if (threadIdx.x == 0) {
+    // sample coordinates are monotone along an axis, so the first / last sample bound the reached pixels
+    const float yf = g.start_h + static_cast<float>(.5f) * g.bin_h / static_cast<float>(G);
+    const float yl = g.start_h + (PH - 1) * g.bin_h + static_cast<float>(G - 1 + .5f) * g.bin_h / static_cast<float>(G);
+    const float xf = g.start_w + static_cast<float>(.5f) * g.bin_w / static_cast<float>(G);
+    const float xl = g.start_w + (PW - 1) * g.bin_w + static_cast<float>(G - 1 + .5f) * g.bin_w / static_cast<float>(G);
+    const bool none = yl < -1.0f || yf > (float)H || xl < -1.0f || xf > (float)W;
+    const int ylo = yf <= 0.f ? 0 : min((int)yf, H - 1), yhi = yl >= (float)(H - 1) ? H - 1 : (int)fmaxf(yl, 0.f) + 1;
+    const int xlo = xf <= 0.f ? 0 : min((int)xf, W - 1), xhi = xl >= (float)(W - 1) ? W - 1 : (int)fmaxf(xl, 0.f) + 1;
+    box[r] = none ? make_int4(1, 0, 1, 0) : make_int4(ylo, yhi, xlo, xhi);
+  }
+}
 
-__global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGrid tg, const float* __restrict__ go,
-                                                           const float* __restrict__ rois, int K, int PH, int PW, int G,
-                                                           int aligned, const int* __restrict__ seg_count,
+__device__ __forceinline__ TapS ld_tap(const TapS* p) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+  TapS t;
+  t.lo = v.x;
+  t.hi = v.y;
+  t.wlo = __int_as_float(v.z);
+  t.whi = __int_as_float(v.w);
+  return t;
+}
+
+__device__ __forceinline__ float tap_weight(const TapS& t, int pix) {
+  return (t.lo == pix ? t.wlo : 0.f) + (t.hi == pix ? t.whi : 0.f);
+}
+
+// (K, C, PP) -> (K, PP, C): the pooled gradient in channel-vector order, so that one bin of one RoI is one coalesced row
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_go(const T* __restrict__ in, T* __restrict__ out, int R, int S) {
+  __shared__ T tile[32][33];
+  const long img = blockIdx.z;
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const T* src = in + img * (long)R * S;
+  T* dst = out + img * (long)R * S;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = r0 + ty + 8 * k, c = s0 + tx;
+    if (r < R && c < S) tile[ty + 8 * k][tx] = src[(long)r * S + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int c = s0 + ty + 8 * k, r = r0 + tx;
+    if (r < R && c < S) dst[(long)c * R + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// Tile-owner gather.  goT is (K, PH*PW, C).  After the candidate list of a 256-RoI round is built (two block barriers),
+// every warp walks the list on its own: no barrier, no shared-memory staging inside the RoI loop.
+__global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGrid tg, const float* __restrict__ goT,
+                                                           const TapS* __restrict__ taps, const int4* __restrict__ box, int K,
+                                                           int PH, int PW, int G, const int* __restrict__ seg_count,
                                                            const int* __restrict__ perm, int chunks) {
-  __shared__ Cand cand[kTileThreads];
-  __shared__ float Ay[TH][kMaxP], Ax[TW][kMaxP];
-  __shared__ unsigned pmask[TH], qmask[TW];
+  __shared__ int cand[kTileThreads];
   __shared__ int wsum[8];
-  __shared__ __align__(16) float sgo[kStageBins * kChunk];
-
   const int C = pv.channels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- which tile ----
   int t = blockIdx.x / chunks;
   const int c0 = (blockIdx.x % chunks) * kChunk;
   int oi = 0;
@@ -248,38 +333,28 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
   t -= b * per_img;
   const int y0 = (t / tg.tiles_x[l]) * TH, x0 = (t % tg.tiles_x[l]) * TW;
   const int H = pv.H[l], W = pv.W[l];
-  const float scale = pv.scale[l];
   const int cc = min(kChunk, C - c0);
   const bool active = 4 * lane < cc;
   const int PP = PH * PW;
+  const int nt = (PH + PW) * G;
   const float invG = 1.0f / (float)G;
+  const int y = y0 + warp;
 
-  float4 acc[TW];
+  u64 acc[TW][2];
 #pragma unroll
-  for (int x = 0; x < TW; x++) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
 
   const int seg = l * pv.batch + b;
   const int nseg = seg_count[seg];
   const int* plist = perm + (long)seg * K;
 
   for (int base = 0; base < nseg; base += kTileThreads) {
-    // ---- candidates of this round, in list order ----
     bool hit = false;
-    Cand me;
-    me.roi = -1;
+    int me = -1;
     if (base + threadIdx.x < nseg) {
-      me.roi = plist[base + threadIdx.x];
-      const RoiGeo<float> g = roi_geometry<float>(rois + 5 * (long)me.roi, scale, PH, PW, G, aligned != 0);
-      me.start_w = g.start_w; me.start_h = g.start_h; me.bin_w = g.bin_w; me.bin_h = g.bin_h;
-      const float yf = g.start_h + static_cast<float>(.5f) * g.bin_h / static_cast<float>(G);
-      const float yl = g.start_h + (PH - 1) * g.bin_h + static_cast<float>(G - 1 + .5f) * g.bin_h / static_cast<float>(G);
-      const float xf = g.start_w + static_cast<float>(.5f) * g.bin_w / static_cast<float>(G);
-      const float xl = g.start_w + (PW - 1) * g.bin_w + static_cast<float>(G - 1 + .5f) * g.bin_w / static_cast<float>(G);
-      // rows/cols any tap can reach (conservative by construction: floor of the first sample .. floor of the last + 1)
-      const bool none = yl < -1.0f || yf > (float)H || xl < -1.0f || xf > (float)W;
-      const int ylo = yf <= 0.f ? 0 : min((int)yf, H - 1), yhi = yl >= (float)(H - 1) ? H - 1 : (int)fmaxf(yl, 0.f) + 1;
-      const int xlo = xf <= 0.f ? 0 : min((int)xf, W - 1), xhi = xl >= (float)(W - 1) ? W - 1 : (int)fmaxf(xl, 0.f) + 1;
-      hit = !none && ylo < y0 + TH && yhi >= y0 && xlo < x0 + TW && xhi >= x0;
+      me = plist[base + threadIdx.x];
+      const int4 bx = __ldg(box + me);
+      hit = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) wsum[warp] = __popc(bal);
@@ -292,109 +367,72 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
     if (hit) cand[pos] = me;
     __syncthreads();
 
-    for (int ci = 0; ci < ncand; ci++) {
-      const Cand cd = cand[ci];
-      // ---- separable tap-weight tables ----
-      for (int e = threadIdx.x; e < TH * PH + TW * PW; e += kTileThreads) {
-        const bool isy = e < TH * PH;
-        const int ee = isy ? e : e - TH * PH;
-        const int P = isy ? PH : PW;
-        const int r = ee / P, p = ee - r * P;
-        const int pix = (isy ? y0 : x0) + r;
-        const int size = isy ? H : W;
-        const float start = isy ? cd.start_h : cd.start_w, bin = isy ? cd.bin_h : cd.bin_w;
-        float w = 0.f;
-        for (int i = 0; i < G; i++) {
-          const float v = start + p * bin + static_cast<float>(i + .5f) * bin / static_cast<float>(G);
-          const AxisTap tp = axis_tap(v, size);
-          if (tp.valid) {
-            if (tp.lo == pix) w += tp.wlo;
-            if (tp.hi == pix) w += tp.whi;
-          }
-        }
-        w *= invG;
-        if (isy) Ay[r][p] = w; else Ax[r][p] = w;
-      }
-      __syncthreads();
-      {
-        const float wy = lane < PH ? Ay[warp][lane] : 0.f;
-        const float wx = lane < PW ? Ax[warp][lane] : 0.f;
-        const unsigned my = __ballot_sync(0xffffffffu, wy != 0.f), mx = __ballot_sync(0xffffffffu, wx != 0.f);
-        if (lane == 0) { pmask[warp] = my; qmask[warp] = mx; }
-      }
-      __syncthreads();
-      unsigned pall = 0, qall = 0;
+    if (y < H) {
+      for (int ci = 0; ci < ncand; ci++) {
+        const int r = cand[ci];
+        const int4 bx = __ldg(box + r);
+        if (y < bx.x || y > bx.y) continue;             // this tile row is outside the RoI's reach (warp-uniform)
+        const TapS* tp = taps + (long)r * nt;
+        // lane p: weight of bin row p on pixel row y ; lane q: weights of bin column q on the 8 pixel columns
+        float wy = 0.f;
+        if (lane < PH)
+          for (int i = 0; i < G; i++) wy += tap_weight(ld_tap(tp + lane * G + i), y);
+        wy *= invG;
+        const unsigned pmask = __ballot_sync(0xffffffffu, wy != 0.f);
+        if (pmask == 0u) continue;
+        float wx[TW];
 #pragma unroll
-      for (int i = 0; i < TH; i++) { pall |= pmask[i]; qall |= qmask[i]; }
-      if (pall == 0 || qall == 0) continue;     // uniform: nothing of this RoI lands in the tile (barriers stay balanced: none below was entered)
-      const int Pa = __ffs(pall) - 1, Pb = 32 - __clz(pall);
-      const int Qa = __ffs(qall) - 1, Qb = 32 - __clz(qall);
-      const int nq = Qb - Qa;
-      const int rows_per_round = kStageBins / nq;       // nq <= 32
-      const unsigned myp = pmask[warp];
-      unsigned qm[TW];
+        for (int x = 0; x < TW; x++) wx[x] = 0.f;
+        if (lane < PW)
+          for (int i = 0; i < G; i++) {
+            const TapS tq = ld_tap(tp + PH * G + lane * G + i);
 #pragma unroll
-      for (int x = 0; x < TW; x++) qm[x] = qmask[x];
-      const float* gsrc = go + ((long)cd.roi * C + c0) * PP;
-
-      for (int pr = Pa; pr < Pb; pr += rows_per_round) {
-        const int np = min(rows_per_round, Pb - pr);
-        const int nb = np * nq;
-        // ---- stage grad_out[r, c0:c0+cc, pr:pr+np, Qa:Qb] -> sgo[bin][channel] ----
-        {
-          const int j = lane & 3, eb = lane >> 2;
-          for (int e0 = 0; e0 < nb; e0 += 8) {
-            const int e = e0 + eb;
-            if (e < nb) {
-              const int pe = e / nq;
-              const float* src = gsrc + (pr + pe) * PW + Qa + (e - pe * nq);
-              for (int cg = warp; 4 * cg < cc; cg += 8) {
-                const int c = 4 * cg + j;
-                sgo[sgo_off(e, c)] = __ldg(src + (long)c * PP);
-              }
-            }
+            for (int x = 0; x < TW; x++) wx[x] += tap_weight(tq, x0 + x);
           }
+        unsigned qm[TW], qall = 0u;
+#pragma unroll
+        for (int x = 0; x < TW; x++) {
+          wx[x] *= invG;
+          qm[x] = __ballot_sync(0xffffffffu, wx[x] != 0.f);
+          qall |= qm[x];
         }
-        __syncthreads();
-        // ---- gather ----
-        if (active) {
-          unsigned pm = myp & (np >= 32 ? 0xffffffffu : (((1u << np) - 1) << pr));
-          while (pm) {
-            const int p = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const float wy = Ay[warp][p];
-            const int erow = (p - pr) * nq - Qa;
+        if (qall == 0u) continue;
+        const float* gr = goT + (long)r * PP * C + c0 + 4 * lane;
+        unsigned pm = pmask;
+        while (pm) {
+          const int p = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const float wyp = __shfl_sync(0xffffffffu, wy, p);
+          const float* grow = gr + (long)p * PW * C;
+          unsigned qq = qall;
+          while (qq) {
+            const int q = __ffs(qq) - 1;
+            qq &= qq - 1;
+            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+            if (active) v = __ldg(reinterpret_cast<const ulonglong2*>(grow + (long)q * C));
 #pragma unroll
             for (int x = 0; x < TW; x++) {
-              unsigned m = qm[x];
-              while (m) {
-                const int q = __ffs(m) - 1;
-                m &= m - 1;
-                const float w = wy * Ax[x][q];
-                const int e = erow + q;
-                const float4 v = *reinterpret_cast<const float4*>(&sgo[e * kChunk + ((lane ^ (e & 7)) << 2)]);
-                acc[x].x = fmaf(w, v.x, acc[x].x);
-                acc[x].y = fmaf(w, v.y, acc[x].y);
-                acc[x].z = fmaf(w, v.z, acc[x].z);
-                acc[x].w = fmaf(w, v.w, acc[x].w);
+              if ((qm[x] >> q) & 1u) {                  // warp-uniform
+                const float w = wyp * __shfl_sync(0xffffffffu, wx[x], q);
+                const u64 w2 = pack2(w, w);
+                acc[x][0] = fma2(w2, v.x, acc[x][0]);
+                acc[x][1] = fma2(w2, v.y, acc[x][1]);
               }
             }
           }
         }
-        __syncthreads();
       }
     }
     __syncthreads();
   }
 
   // ---- the tile's gradient: written exactly once ----
-  const int y = y0 + warp;
   if (active && y < H) {
-    float4* dst = reinterpret_cast<float4*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
     const long C4 = C >> 2;
 #pragma unroll
     for (int x = 0; x < TW; x++)
-      if (x0 + x < W) dst[x * C4] = acc[x];
+      if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
   }
 }
 
@@ -404,9 +442,28 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 using namespace cpm;
 
-extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch) {
-  const size_t segs = (size_t)(num_levels > 0 ? num_levels : 1) * (size_t)(batch > 0 ? batch : 1);
-  return align256(segs * sizeof(int)) + align256(segs * (size_t)(K > 0 ? K : 1) * sizeof(int));
+struct BwdWs {
+  size_t seg_count, perm, taps, box, goT, total;
+};
+
+static BwdWs bwd_layout(int64_t K, int L, int B, int C, int PH, int PW, int G) {
+  BwdWs w;
+  const size_t segs = (size_t)(L > 0 ? L : 1) * (size_t)(B > 0 ? B : 1);
+  const size_t k = (size_t)(K > 0 ? K : 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  w.seg_count = take(segs * sizeof(int));
+  w.perm = take(segs * k * sizeof(int));
+  w.taps = take(k * (size_t)(PH + PW) * (size_t)(G > 0 ? G : 1) * sizeof(TapS));
+  w.box = take(k * sizeof(int4));
+  w.goT = take(k * (size_t)C * PH * PW * sizeof(float));
+  w.total = off;
+  return w;
+}
+
+extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
+                                                         int pooled_w, int sampling_ratio) {
+  return bwd_layout(K, num_levels, batch, channels, pooled_h, pooled_w, sampling_ratio).total;
 }
 
 extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
@@ -449,18 +506,33 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
                 "sampling_ratio >= 1 and pooled size <= %d; use CPM_BWD_ATOMIC otherwise", kMaxP);
       return CPM_ERR_UNSUPPORTED;
     }
-    const size_t need = cpm_roi_align_backward_workspace_bytes(K, L, B);
-    if (d_workspace == nullptr || workspace_bytes < need) {
-      set_error("workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    const BwdWs w = bwd_layout(K, L, B, C, pooled_h, pooled_w, sampling_ratio);
+    if (d_workspace == nullptr || workspace_bytes < w.total) {
+      set_error("workspace too small: %zu < %zu bytes", workspace_bytes, w.total);
       return CPM_ERR_WORKSPACE;
     }
     if ((rc = check_device_ptr(d_workspace, "workspace")) != CPM_OK) return rc;
-    int* seg_count = (int*)d_workspace;
-    int* perm = (int*)((char*)d_workspace + align256((size_t)L * B * sizeof(int)));
+    char* wsb = (char*)d_workspace;
+    int* seg_count = (int*)(wsb + w.seg_count);
+    int* perm = (int*)(wsb + w.perm);
+    TapS* taps = (TapS*)(wsb + w.taps);
+    int4* box = (int4*)(wsb + w.box);
+    float* goT = (float*)(wsb + w.goT);
     const int Kp = K > 0 ? (int)K : 1;
+    const int PP = pooled_h * pooled_w;
     if (K > 0) {
       bwd_bin_rois<<<L * B, 256, 0, st>>>(pv, (const float*)d_rois, (int)K, mp, d_roi_levels, seg_count, perm);
       CPM_CHECK_LAUNCH();
+      bwd_roi_taps<<<(unsigned)K, 64, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w, sampling_ratio, aligned,
+                                               mp, d_roi_levels, taps, box);
+      CPM_CHECK_LAUNCH();
+      // grad_out (K, C, PP) -> (K, PP, C)
+      for (long k0 = 0; k0 < K; k0 += 32768) {
+        const int kb = (int)((K - k0) < 32768 ? (K - k0) : 32768);
+        dim3 grid((PP + 31) / 32, (C + 31) / 32, kb);
+        transpose_go<float><<<grid, 256, 0, st>>>((const float*)d_grad_out + k0 * (long)C * PP, goT + k0 * (long)C * PP, C, PP);
+        CPM_CHECK_LAUNCH();
+      }
     } else {
       CPM_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, (size_t)L * B * sizeof(int), st));
     }
@@ -476,9 +548,8 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
     }
     for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
-    bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, (const float*)d_grad_out, (const float*)d_rois,
-                                                                  Kp, pooled_h, pooled_w, sampling_ratio, aligned,
-                                                                  seg_count, perm, chunks);
+    bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, goT, taps, box, Kp, pooled_h, pooled_w,
+                                                                  sampling_ratio, seg_count, perm, chunks);
     CPM_CHECK_LAUNCH();
     return CPM_OK;
   }

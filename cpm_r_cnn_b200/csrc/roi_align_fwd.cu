@@ -308,6 +308,269 @@ __global__ void __launch_bounds__(32 * 7, 2) roi_align_fwd_nhwc_rows(PyramidView
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Column-sweep kernel (sampling_ratio 2; any pooled size up to 32x32): the hot path of the CPM head's poolers.
+//
+// One CTA = (RoI, 128-channel chunk, group of <= 7 bin rows); a warp owns one bin row, a lane 4 channels.  The warp walks
+// the feature COLUMNS its row touches from left to right.  Per step it issues the loads of the next kColBatch columns
+// of the four feature rows of its two sample rows (y_low/y_high of iy = 0, 1) as one unconditional batch -- 8
+// independent 512-byte row loads in flight per warp -- and then consumes every sample whose x_low is one of those
+// columns (a warp-uniform walk over the RoI's x-tap table in shared memory).  Every feature pixel of the band is
+// loaded exactly once per bin row; both sample rows and all sample columns that share it are served from registers.
+// The four samples of a bin are summed in the reference's order ((v00 + v01) + v10) + v11 (ROIAlign_cuda.cu:234-252).
+// Finished bins go to a swizzled shared-memory tile [bin][channel]; the tile leaves as (4 channels x 8 bins) patches:
+// bank-conflict-free reads, 32-byte-segment global writes into the reference's (K, C, PH, PW) layout.
+constexpr int kRowsPerCta = 7;
+constexpr int kColBatch = 2;
+
+typedef unsigned long long u64;
+
+// packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): two IEEE-rounded fp32 operations per instruction, bit-identical
+// to the scalar forms -- halves the issue slots of the bilinear math
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+struct V4 {          // 4 channels as two fp32x2 pairs
+  u64 lo, hi;
+};
+struct Col4 {
+  V4 r[4];
+};
+struct __align__(16) W8 {      // the four bilinear weights of one (sample row, sample column), each duplicated for fp32x2
+  u64 w1, w2, w3, w4;
+};
+
+__device__ __forceinline__ V4 ldg_v4(const char* p) {
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  V4 r;
+  r.lo = v.x;
+  r.hi = v.y;
+  return r;
+}
+
+// w1*v1 + w2*v2 + w3*v3 + w4*v4, reference order, contracted as mul, fma, fma, fma (see tap4)
+__device__ __forceinline__ V4 bilin4(const W8& w, const V4& v1, const V4& v2, const V4& v3, const V4& v4) {
+  V4 r;
+  r.lo = fma2(w.w4, v4.lo, fma2(w.w3, v3.lo, fma2(w.w2, v2.lo, mul2(w.w1, v1.lo))));
+  r.hi = fma2(w.w4, v4.hi, fma2(w.w3, v3.hi, fma2(w.w2, v2.hi, mul2(w.w1, v1.hi))));
+  return r;
+}
+__device__ __forceinline__ V4 add4(const V4& a, const V4& b) {
+  V4 r;
+  r.lo = add2(a.lo, b.lo);
+  r.hi = add2(a.hi, b.hi);
+  return r;
+}
+
+__global__ void __launch_bounds__(32 * kRowsPerCta, 2) roi_align_fwd_nhwc_sweep(
+    PyramidView pv, const float* __restrict__ rois, int PH, int PW, int aligned, MapperView mp,
+    const int* __restrict__ roi_levels, float* __restrict__ out, int chunks, int rgroups) {
+  constexpr int G = 2;
+  constexpr int kMaxS = kMaxRowsPH * G;
+  extern __shared__ __align__(16) float smem_dyn[];
+  // dynamic: W8 wtab[nrows*G][NS] | float tile[kChunk][nbp]
+  __shared__ int xlo[kMaxS];
+  __shared__ TapS xt[kMaxS];
+  __shared__ TapS yt[kRowsPerCta * G];
+  __shared__ int s_range[2];
+  const int C = pv.channels;
+  const int rg = blockIdx.x % rgroups;
+  const int chunk = (blockIdx.x / rgroups) % chunks;
+  const long n = blockIdx.x / (rgroups * chunks);
+  const int c0 = chunk * kChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cc = min(kChunk, C - c0);
+  const int ph0 = rg * kRowsPerCta;
+  const int nrows = min(kRowsPerCta, PH - ph0);
+  const int NS = PW * G;
+  const int nb = nrows * PW;
+  const int nbp = (kRowsPerCta * PW) | 1;             // odd row stride of the staging tile
+  W8* wtab = reinterpret_cast<W8*>(smem_dyn);
+  float* tile = smem_dyn + (size_t)kRowsPerCta * G * NS * (sizeof(W8) / sizeof(float));
+  const float* roi = rois + 5 * n;
+  const int l = roi_level(roi, pv, mp, roi_levels, n);
+  const bool lvl_ok = l >= 0 && l < pv.num_levels;
+  if (lvl_ok) {
+    const int H = pv.H[l], W = pv.W[l];
+    const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
+    // ---- per-CTA tables: axis taps, then the 4 weights of every (sample row, sample column) ----
+    for (int e = threadIdx.x; e < NS + nrows * G; e += blockDim.x) {
+      const bool isx = e < NS;
+      const int k = isx ? e : e - NS + ph0 * G;
+      const int p = k / G, i = k % G;
+      const float start = isx ? g.start_w : g.start_h, bin = isx ? g.bin_w : g.bin_h;
+      const float v = start + p * bin + static_cast<float>(i + .5f) * bin / static_cast<float>(G);
+      if (isx) {
+        const TapS t = make_tap(v, W);
+        xt[k] = t;
+        xlo[k] = t.lo;
+      } else {
+        yt[k - ph0 * G] = make_tap(v, H);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {          // valid samples are one contiguous run (coordinates are monotone)
+      int sb = 0, se = NS;
+      while (sb < NS && xlo[sb] < 0) sb++;
+      while (se > sb && xlo[se - 1] < 0) se--;
+      s_range[0] = sb;
+      s_range[1] = se;
+    }
+    for (int e = threadIdx.x; e < nrows * G * NS; e += blockDim.x) {
+      const TapS ty = yt[e / NS], tx = xt[e % NS];
+      const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+      W8 w;
+      w.w1 = pack2(w1, w1); w.w2 = pack2(w2, w2); w.w3 = pack2(w3, w3); w.w4 = pack2(w4, w4);
+      wtab[e] = w;
+    }
+    __syncthreads();
+    if (warp < nrows && 4 * lane < cc) {
+      const TapS ty0 = yt[warp * G], ty1 = yt[warp * G + 1];
+      const bool yv0 = ty0.lo >= 0, yv1 = ty1.lo >= 0;
+      const size_t stride = (size_t)C * sizeof(float);                 // bytes per pixel
+      const char* f = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (long)g.b * H * W * C + c0 + 4 * lane);
+      const char* p0 = f + (size_t)(yv0 ? ty0.lo : 0) * W * stride;
+      const char* p1 = f + (size_t)(yv0 ? ty0.hi : 0) * W * stride;
+      const char* p2 = f + (size_t)(yv1 ? ty1.lo : 0) * W * stride;
+      const char* p3 = f + (size_t)(yv1 ? ty1.hi : 0) * W * stride;
+      const W8* w0 = wtab + (warp * G) * NS;
+      const W8* w1t = w0 + NS;
+      float* trow = tile + warp * PW;
+      const int cch = 4 * lane;
+      float* t0 = trow + (cch + 0) * nbp + (cch >> 5);
+      float* t1p = trow + (cch + 1) * nbp + (cch >> 5);
+      float* t2 = trow + (cch + 2) * nbp + (cch >> 5);
+      float* t3 = trow + (cch + 3) * nbp + (cch >> 5);
+      const int s_begin = s_range[0], s_end = s_range[1];
+      V4 s0, t1;
+      s0.lo = s0.hi = t1.lo = t1.hi = 0ull;            // +0.0f pairs
+      const V4 zero4 = s0;
+
+      auto load_col = [&](int x, int xmax) {
+        const size_t xo = (size_t)min(x, xmax) * stride;
+        Col4 c;
+        c.r[0] = ldg_v4(p0 + xo);
+        c.r[1] = ldg_v4(p1 + xo);
+        c.r[2] = ldg_v4(p2 + xo);
+        c.r[3] = ldg_v4(p3 + xo);
+        return c;
+      };
+      auto flush = [&](int pw, const V4& v) {
+        const float2 a = unpack2(v.lo), b = unpack2(v.hi);
+        t0[pw] = a.x * 0.25f;
+        t1p[pw] = a.y * 0.25f;
+        t2[pw] = b.x * 0.25f;
+        t3[pw] = b.y * 0.25f;
+      };
+      auto skip_sample = [&](int sx) {        // out-of-range sample: adds 0 (ROIAlign_cuda.cu:46-49)
+        if (sx & 1) flush(sx >> 1, add4(s0, t1)); else { s0 = zero4; t1 = zero4; }
+      };
+      auto take_sample = [&](int sx, const Col4& ca, const Col4& cb) {
+        V4 va = zero4, vb = zero4;
+        if (yv0) va = bilin4(w0[sx], ca.r[0], cb.r[0], ca.r[1], cb.r[1]);
+        if (yv1) vb = bilin4(w1t[sx], ca.r[2], cb.r[2], ca.r[3], cb.r[3]);
+        if (sx & 1) {
+          flush(sx >> 1, add4(add4(add4(s0, va), t1), vb));    // ((v00 + v01) + v10) + v11
+        } else {
+          s0 = va;
+          t1 = vb;
+        }
+      };
+
+      int s = 0;
+      for (; s < s_begin; s++) skip_sample(s);
+      if (s < s_end) {
+        const int xmax = xt[s_end - 1].hi;         // right-most column any sample needs
+        int col = xlo[s];
+        Col4 c[kColBatch + 1];
+        c[0] = load_col(col, xmax);
+        while (s < s_end) {
+#pragma unroll
+          for (int k = 1; k <= kColBatch; k++) c[k] = load_col(col + k, xmax);
+#pragma unroll
+          for (int k = 0; k < kColBatch; k++) {
+            while (s < s_end && xlo[s] == col + k) {
+              take_sample(s, c[k], c[k + 1]);
+              s++;
+            }
+          }
+          c[0] = c[kColBatch];
+          col += kColBatch;
+          if (s < s_end) {
+            const int nl = xlo[s];
+            if (nl > col) {          // sample spacing > 2 pixels: jump over untouched columns
+              col = nl;
+              c[0] = load_col(col, xmax);
+            }
+          }
+        }
+      }
+      for (; s < NS; s++) skip_sample(s);
+    }
+  } else {
+    for (int e = threadIdx.x; e < kChunk * nbp + 4; e += blockDim.x) tile[e] = 0.f;
+  }
+  __syncthreads();
+  // ---- tile -> out[n, c0:c0+cc, ph0:ph0+nrows, :]  (nb contiguous floats per channel) ----
+  {
+    const int PP = PH * PW;
+    float* o = out + ((long)n * C + c0) * PP + ph0 * PW;
+    for (int c = warp; c < cc; c += kRowsPerCta) {
+      const float* tr = tile + c * nbp + (c >> 5);
+      float* oc = o + (long)c * PP;
+      for (int e = lane; e < nb; e += 32) oc[e] = tr[e];
+    }
+  }
+}
+
+static size_t sweep_smem_bytes(int PW) {
+  const int NS = PW * 2;
+  return (size_t)kRowsPerCta * 2 * NS * sizeof(W8) + (size_t)(kChunk * ((kRowsPerCta * PW) | 1) + 8) * sizeof(float);
+}
+
+static int launch_sweep(const PyramidView& pv, const float* rois, long K, int PH, int PW, int aligned, const MapperView& mp,
+                        const int* lv, float* out, cudaStream_t st) {
+  const int chunks = (pv.channels + kChunk - 1) / kChunk;
+  const int rgroups = (PH + kRowsPerCta - 1) / kRowsPerCta;
+  const size_t smem = sweep_smem_bytes(PW);
+  static thread_local int configured_dev = -1;
+  int dev;
+  CPM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(roi_align_fwd_nhwc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dev = dev;
+  }
+  const long blocks = K * chunks * rgroups;
+  CPM_CHECK_ARG(blocks < (1L << 31), "too many RoIs for one launch");
+  roi_align_fwd_nhwc_sweep<<<(unsigned)blocks, 32 * kRowsPerCta, smem, st>>>(pv, rois, PH, PW, aligned, mp, lv, out, chunks,
+                                                                            rgroups);
+  CPM_CHECK_LAUNCH();
+  return CPM_OK;
+}
+
 template <int PW, int G>
 static int launch_rows(const PyramidView& pv, const float* rois, long K, int PH, int aligned, const MapperView& mp,
                        const int* lv, float* out, cudaStream_t st) {
@@ -381,11 +644,16 @@ extern "C" int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_ro
   const int PP = pooled_h * pooled_w;
   const size_t smem_any = (size_t)(kChunk * (PP | 1) + 8) * sizeof(float);
   if (smem_any > 200 * 1024) nhwc_ok = false;
-  if (impl == CPM_FWD_NHWC && !nhwc_ok) {
+  if ((impl == CPM_FWD_NHWC || impl == CPM_FWD_NHWC_ROWS) && !nhwc_ok) {
     set_error("CPM_FWD_NHWC needs an NHWC fp32 pyramid, bilinear interpolation, C %% 4 == 0 and 16-byte aligned maps");
     return CPM_ERR_UNSUPPORTED;
   }
   if (nhwc_ok && impl != CPM_FWD_GENERIC) {
+    bool small_maps = true;     // the sweep kernel indexes a level with 32-bit float4 offsets
+    for (int l = 0; l < feat->num_levels; l++)
+      small_maps = small_maps && (double)feat->batch * feat->height[l] * feat->width[l] * feat->channels < 8.0e9;
+    if (sampling_ratio == 2 && pooled_w <= kMaxRowsPH && pooled_h <= kMaxRowsPH && small_maps && impl != CPM_FWD_NHWC_ROWS)
+      return launch_sweep(pv, (const float*)d_rois, K, pooled_h, pooled_w, aligned, mp, d_roi_levels, (float*)d_out, st);
     if (sampling_ratio == 2 && pooled_w == 7 && pooled_h <= kMaxRowsPH)
       return launch_rows<7, 2>(pv, (const float*)d_rois, K, pooled_h, aligned, mp, d_roi_levels, (float*)d_out, st);
     if (sampling_ratio == 2 && pooled_w == 14 && pooled_h <= kMaxRowsPH)

@@ -114,7 +114,7 @@ def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_rat
     ws, ws_bytes = None, 0
     with _lib.device_of(grad_output):
         if use == _lib.BWD_DETERMINISTIC:
-            ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes(K, len(shapes), B))
+            ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes(K, len(shapes), B, C, ph, pw, int(sampling_ratio)))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         _lib.check(_lib.lib().cpm_roi_align_backward(ctypes.byref(pyr), _lib.ptr(grad_output), _lib.ptr(rois), K, ph, pw,
                                                      int(sampling_ratio), int(bool(aligned)), interpolation,

@@ -63,7 +63,8 @@ extern "C" {
 /* forward implementation selector (testing / benchmarking aid; AUTO is what callers use) */
 #define CPM_FWD_AUTO 0
 #define CPM_FWD_GENERIC 1         /* one thread per output element, any parameters / layout, fp32/fp64 */
-#define CPM_FWD_NHWC 2            /* warp-per-bin-row channel-vector gather (bilinear, NHWC, fp32/bf16, C % 4 == 0) */
+#define CPM_FWD_NHWC 2            /* warp-per-bin-row channel-vector gather (bilinear, NHWC, fp32, C % 4 == 0) */
+#define CPM_FWD_NHWC_ROWS 3       /* the earlier register-row variant of CPM_FWD_NHWC (kept for A/B measurements) */
 
 /*
  * A feature pyramid (or the pyramid of dense feature gradients): L levels of dense maps that share batch
@@ -123,8 +124,10 @@ CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois,
  * `grad_feat` describes the OUTPUT maps: every level is fully written (dense gradient, zeros where no RoI
  * reaches -- the reference's at::zeros + atomicAdd, :451-452,:340-347), also when K == 0.
  *   mode        CPM_BWD_DETERMINISTIC (needs the workspace) | CPM_BWD_ATOMIC
- * Workspace: cpm_roi_align_backward_workspace_bytes(K, num_levels) bytes, 256-byte aligned. */
-CPM_API size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch);
+ * Workspace (deterministic mode): cpm_roi_align_backward_workspace_bytes(...) bytes, 256-byte aligned; it holds the
+ * per-(level,image) RoI lists, the per-RoI tap tables and the channel-vector copy (K, PH*PW, C) of grad_out. */
+CPM_API size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
+                                                      int pooled_w, int sampling_ratio);
 CPM_API int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
                            int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
                            const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode,

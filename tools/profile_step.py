@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--nms", action="store_true")
 ap.add_argument("--mode", default="deterministic")
+ap.add_argument("--impl", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 rois_h, feats_h, gouts_h = bench.make_workload(0)
@@ -26,11 +27,26 @@ rois = rois_h.to(dev)
 gouts = [g.to(dev) for g in gouts_h]
 shapes = [tuple(f.shape) for f in feats_h]
 mapper = _lib.make_mapper(2, 5)
+tot = {}
 for i in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    k = 0
     for p, go in zip(bench.POOLERS, gouts):
-        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper)
+        evs[k].record()
+        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl)
+        evs[k + 1].record()
         grads = pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode)
+        k += 2
+    evs[k].record()
     torch.cuda.synchronize()
+    if i >= 2:
+        for j, n in enumerate(["fwd7", "bwd7", "fwd14", "bwd14"]):
+            tot.setdefault(n, []).append(evs[j].elapsed_time(evs[j + 1]))
+if tot:
+    ab = bench.algorithmic_bytes(rois_h)
+    for n, v in tot.items():
+        ms = sorted(v)[len(v) // 2]
+        print("%-6s median %.4f ms  min %.4f ms   %.0f GB/s  frac %.3f" % (n, ms, min(v), ab[n] / ms / 1e6, ab[n] / ms / 1e6 / 6540.8))
 if args.nms:
     gen = torch.Generator().manual_seed(1000)
     b, s, seg = sy.rpn_like_candidates(gen, 16, 5, 1000)
