@@ -593,6 +593,9 @@ static int launch_rows(const PyramidView& pv, const float* rois, long K, int PH,
 }
 
 int check_device_ptr(const void* p, const char* what);
+bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, int sampling_ratio, const void* d_out);
+int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
+                    const int* lv, float* out, cudaStream_t st);
 
 int check_pyramid(const cpm_pyramid_t* p, const char* what) {
   CPM_CHECK_ARG(p != nullptr, "%s is NULL", what);
@@ -644,6 +647,15 @@ extern "C" int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_ro
   const int PP = pooled_h * pooled_w;
   const size_t smem_any = (size_t)(kChunk * (PP | 1) + 8) * sizeof(float);
   if (smem_any > 200 * 1024) nhwc_ok = false;
+  const bool cols_ok = nhwc_ok && interpolation == CPM_INTERP_BILINEAR &&
+                       fwd_cols_supported(feat, pooled_h, pooled_w, sampling_ratio, d_out);
+  if (impl == CPM_FWD_COLS && !cols_ok) {
+    set_error("CPM_FWD_COLS needs an NHWC fp32 pyramid, bilinear interpolation, a 7x7 or 14x14 pooler, sampling_ratio 1 or 2 "
+              "and C %% 128 == 0 (7x7) / C %% 64 == 0 (14x14)");
+    return CPM_ERR_UNSUPPORTED;
+  }
+  if (cols_ok && (impl == CPM_FWD_AUTO || impl == CPM_FWD_COLS))
+    return launch_fwd_cols(pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, (float*)d_out, st);
   if ((impl == CPM_FWD_NHWC || impl == CPM_FWD_NHWC_ROWS) && !nhwc_ok) {
     set_error("CPM_FWD_NHWC needs an NHWC fp32 pyramid, bilinear interpolation, C %% 4 == 0 and 16-byte aligned maps");
     return CPM_ERR_UNSUPPORTED;

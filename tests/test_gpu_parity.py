@@ -115,6 +115,61 @@ def test_roi_align_impl_paths_agree():
     close(a.cpu(), b.cpu(), 1e-6)
 
 
+def _size_sweep_rois(seed, B, img=(200, 336)):
+    """RoIs whose side runs from a fraction of a pixel to several times the image (every bins-per-pixel regime of the
+    column-table kernel: NW = 2, 4 and 7), half of them sticking out of the image, plus the adversarial rows."""
+    gen = torch.Generator().manual_seed(seed)
+    sides = torch.cat([torch.tensor([0.3, 0.9, 1.7, 2.5, 3.9, 5.0, 7.7, 11.0, 14.0, 19.0, 27.0, 41.0, 60.0, 97.0, 160.0,
+                                     333.0, 700.0, 1500.0]), torch.exp(torch.empty(40).uniform_(0.0, 6.5, generator=gen))])
+    n = sides.numel()
+    ar = torch.exp(torch.empty(n).uniform_(np.log(0.3), np.log(3.0), generator=gen))
+    w, h = sides * torch.sqrt(ar), sides / torch.sqrt(ar)
+    cx = (torch.rand(n, generator=gen) * 1.4 - 0.2) * img[1]
+    cy = (torch.rand(n, generator=gen) * 1.4 - 0.2) * img[0]
+    ids = (torch.arange(n) % B).float()
+    rois = torch.stack([ids, cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    return torch.cat([rois, synthetic.adversarial_rois(img[0], img[1], B)], 0)
+
+
+@pytest.mark.parametrize("P,C", [(7, 128), (7, 256), (14, 64), (14, 256)])
+@pytest.mark.parametrize("sr,aligned", [(2, False), (1, False), (2, True)])
+def test_roi_align_cols_kernel(P, C, sr, aligned):
+    """The column-table forward kernel (CPM_FWD_COLS: 7x7 / 14x14, sampling_ratio 1|2) on every level scale, all RoI
+    size regimes, against the oracle and against the reference-shaped generic kernel."""
+    B = 2
+    gen = torch.Generator().manual_seed(100 + P + C + sr)
+    feats = synthetic.pyramid(gen, B, C, 200, 336)
+    rois = _size_sweep_rois(P * 10 + sr, B)
+    if aligned:
+        rois = rois[(rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])]
+    for l in (0, 1, 3):
+        f = feats[l].cuda().contiguous(memory_format=torch.channels_last)
+        out = pooler_forward([f], [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, impl=_lib.FWD_COLS)
+        gen_out = pooler_forward([f], [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, impl=_lib.FWD_GENERIC)
+        close(out.cpu(), gen_out.cpu())
+        sub = slice(0, None, 3)       # the oracle is scalar C: check a third of the RoIs against it
+        ref = oracle.roi_align_forward(feats[l].numpy(), rois.numpy()[sub], SCALES[l], P, P, sr, aligned)
+        close(out.cpu().numpy()[sub], ref)
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_roi_align_cols_kernel_multilevel(P):
+    """Fused level mapping inside the column-table kernel: COCO-shaped RoIs over the 4-level pyramid, C = 256."""
+    B, C = 2, 256
+    gen = torch.Generator().manual_seed(77)
+    feats = synthetic.pyramid(gen, B, C, 200, 336)
+    rois = torch.cat([synthetic.coco_like_rois(gen, 64, B, 200, 336), _size_sweep_rois(5, B)], 0)
+    xs = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    m = _lib.make_mapper(2, 5)
+    out = pooler_forward(xs, SCALES, rois.cuda(), (P, P), 2, False, 0, m, impl=_lib.FWD_COLS)
+    levels = oracle.level_map(rois.numpy(), 2, 5)
+    ref = np.zeros(out.shape, np.float32)
+    for l in range(4):
+        idx = np.nonzero(levels == l)[0]
+        ref[idx] = oracle.roi_align_forward(feats[l].numpy(), rois.numpy()[idx], SCALES[l], P, P, 2, False)
+    close(out.cpu(), ref)
+
+
 def test_roi_align_nearest_and_errors():
     feats, rois = _random_case(7, 1, 8, 8)
     rois[:, 0] = 0

@@ -17,6 +17,7 @@ import cpm_r_cnn_b200 as ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--nms", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (no host enqueue cost in the numbers)")
 ap.add_argument("--mode", default="deterministic")
 ap.add_argument("--impl", type=int, default=0)
 args = ap.parse_args()
@@ -28,6 +29,30 @@ gouts = [g.to(dev) for g in gouts_h]
 shapes = [tuple(f.shape) for f in feats_h]
 mapper = _lib.make_mapper(2, 5)
 tot = {}
+if args.graph:
+    ops_ = []
+    for p, go in zip(bench.POOLERS, gouts):
+        ops_.append(lambda p=p: pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl))
+        ops_.append(lambda p=p, go=go: pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode))
+    for f in ops_:
+        f(); f()
+    torch.cuda.synchronize()
+    graphs, keep = [], []
+    for f in ops_:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep.append(f())
+        graphs.append(g)
+    for i in range(args.steps + 3):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for j, g in enumerate(graphs):
+            evs[j].record(); g.replay()
+        evs[4].record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            for j, n in enumerate(["fwd7", "bwd7", "fwd14", "bwd14"]):
+                tot.setdefault(n, []).append(evs[j].elapsed_time(evs[j + 1]))
+    args.steps = 0
 for i in range(args.steps):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     k = 0
