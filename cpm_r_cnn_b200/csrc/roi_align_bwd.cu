@@ -436,6 +436,324 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// deterministic tile-owner gather, staged: the single-pass kernel (no channel-vector copy of grad_out in HBM)
+// ------------------------------------------------------------------------------------------------------------------
+// One CTA per 8x8-pixel tile x 128-channel chunk, a warp per tile row, a lane per 4 channels (as bwd_tiles).  For every
+// RoI that reaches the tile, in RoI-index order, the CTA
+//   - clips the RoI's bins to those with a tap inside the tile (rows pA..pB, columns qA..qB),
+//   - stages that sub-block of grad_out[r, c0:c0+128, :, :] in shared memory as channel-vector rows S[bin][128 ch] with
+//     cp.async: 4-byte copies that transpose the reference's (K, C, PH, PW) layout on the fly (16-byte copies when the
+//     pooled gradient is channels-last), double-buffered so the copies of the next sub-block fly under the arithmetic of
+//     the current one (at most NBUF bins per buffer; larger sub-blocks are split by bin rows),
+//   - builds the dense separable weight tables WY[tile row][bin row], WX[bin column][tile column]
+//     (bilinear_interpolate_gradient :113-171 factors per axis), and
+//   - accumulates  g[y][x][c] += sum_q WX[q][x] * (sum_p WY[y][p] * S[p][q][c])  in registers (packed FFMA2), vertical
+//     combine first, in a fixed order: deterministic, no atomics.
+namespace bst {
+
+constexpr int NBUF = 56;               // bins per staging buffer (4 bin rows of a 14-wide pooler)
+constexpr int SROW = kChunk + 4;       // floats per staged bin (528 B: rows stay 16-byte aligned, 4-byte stores conflict-free)
+constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the tables hold (the path needs P * G <= 32)
+
+struct __align__(16) Item {
+  long long gofs;                      // float offset of the sub-block's first element inside grad_out
+  int r, p0, np, q0, nq, nb;
+  unsigned magic;                      // pq / nq == (pq * magic) >> 16 for pq < 64, nq <= 32
+  int valid;
+  int pad[2];
+};
+
+struct Smem {
+  float S[2][NBUF * SROW];
+  float2 WX[2][MAXQ][TW];              // weights duplicated for FFMA2
+  float2 WY[2][TH][MAXP];
+  int2 prange[2][TH];                  // first / last bin row of the item with weight on the tile row
+  Item ring[4];
+  int cand[kTileThreads];
+  int crange[kTileThreads];            // pA | pB << 8 | qA << 16 | qB << 24, or -1
+  int wsum[8];
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// GO_CL: grad_out is (K, PH, PW, C) (a channels_last pooled gradient); otherwise (K, C, PH, PW) contiguous.
+// PC / GC: compile-time pooled size (PH == PW == PC) and sampling grid, 0 = runtime values.
+template <bool GO_CL, int PC, int GC>
+__global__ void __launch_bounds__(kTileThreads, 3)
+bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, const TapS* __restrict__ taps,
+                 const int4* __restrict__ box, int K, int PH_, int PW_, int G_, const int* __restrict__ seg_count,
+                 const int* __restrict__ perm, int chunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int PH = PC ? PC : PH_, PW = PC ? PC : PW_, G = GC ? GC : G_;
+  const int C = pv.channels;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int t = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * kChunk;
+  int oi = 0;
+  while (oi + 1 < pv.num_levels && t >= tg.first[oi + 1]) oi++;
+  const int l = tg.order[oi];
+  t -= tg.first[oi];
+  const int per_img = tg.tiles_x[l] * tg.tiles_y[l];
+  const int b = t / per_img;
+  t -= b * per_img;
+  const int y0 = (t / tg.tiles_x[l]) * TH, x0 = (t % tg.tiles_x[l]) * TW;
+  const int H = pv.H[l], W = pv.W[l];
+  const int cc = min(kChunk, C - c0);
+  const bool active = 4 * lane < cc;
+  const int PP = PH * PW;
+  const int nt = (PH + PW) * G;
+  const float invG = 1.0f / (float)G;
+  const int y = y0 + warp;
+
+  u64 acc[TW][2];
+#pragma unroll
+  for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
+
+  const int seg = l * pv.batch + b;
+  const int nseg = seg_count[seg];
+  const int* plist = perm + (long)seg * K;
+
+  // staging constants of this thread
+  //   transposing 4-byte copies: lane = (channel cl of a group of 4, bin j of a group of 8); the warp takes channel
+  //   groups warp, warp + 8, warp + 16, warp + 24, i.e. channels cth + 32 k
+  const int cl = lane & 3, j = lane >> 2;
+  const int cth = 4 * warp + cl;
+  const uint32_t s_base = smem_u32(&sm.S[0][0]);
+  constexpr uint32_t kBufBytes = NBUF * SROW * 4;
+
+  for (int base = 0; base < nseg; base += kTileThreads) {
+    // ---- RoIs of this (level, image) whose reach intersects the tile, in RoI order ----
+    bool hit = false;
+    int me = -1;
+    if (base + threadIdx.x < nseg) {
+      me = plist[base + threadIdx.x];
+      const int4 bx = __ldg(box + me);
+      hit = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) sm.wsum[warp] = __popc(bal);
+    __syncthreads();
+    int pos = __popc(bal & ((1u << lane) - 1)), ncand = 0;
+    for (int w = 0; w < 8; w++) {
+      if (w < warp) pos += sm.wsum[w];
+      ncand += sm.wsum[w];
+    }
+    if (hit) sm.cand[pos] = me;
+    __syncthreads();
+    if (ncand == 0) continue;            // (uniform) nothing reaches the tile in this round
+    // ---- per candidate: the bin rows / columns with a sample tap inside the tile (lane = sample) ----
+    for (int ci = warp; ci < ncand; ci += 8) {
+      const TapS* tp = taps + (long)sm.cand[ci] * nt;
+      bool ty = false, tx = false;
+      if (lane < PH * G) {
+        const TapS s = ld_tap(tp + lane);
+        ty = s.lo >= 0 && s.hi >= y0 && s.lo < y0 + TH;
+      }
+      if (lane < PW * G) {
+        const TapS s = ld_tap(tp + PH * G + lane);
+        tx = s.lo >= 0 && s.hi >= x0 && s.lo < x0 + TW;
+      }
+      const unsigned my = __ballot_sync(0xffffffffu, ty), mx = __ballot_sync(0xffffffffu, tx);
+      if (lane == 0) {
+        int cr = -1;
+        if (my != 0u && mx != 0u) {
+          const int pA = (__ffs(my) - 1) / G, pB = (31 - __clz(my)) / G;
+          const int qA = (__ffs(mx) - 1) / G, qB = (31 - __clz(mx)) / G;
+          cr = pA | (pB << 8) | (qA << 16) | (qB << 24);
+        }
+        sm.crange[ci] = cr;
+      }
+    }
+    __syncthreads();
+
+    // ---- the sub-blocks ("items") of the round: thread 0 walks the candidates and publishes descriptors two items
+    //      ahead in a 4-slot ring; everybody else only reads them ----
+    int gci = 0, gp = 0;                 // generator state (thread 0)
+    auto generate = [&](Item& out) {
+      for (;;) {
+        if (gci >= ncand) {
+          out.valid = 0;
+          return;
+        }
+        const int cr = sm.crange[gci];
+        if (cr >= 0) {
+          const int pA = cr & 255, pB = (cr >> 8) & 255, qA = (cr >> 16) & 255, qB = (cr >> 24) & 255;
+          if (gp < pA) gp = pA;
+          if (gp <= pB) {
+            const int nq = qB - qA + 1;
+            const int np = min(min(MAXP, NBUF / nq), pB - gp + 1);
+            const int r = sm.cand[gci];
+            out.r = r;
+            out.p0 = gp;
+            out.np = np;
+            out.q0 = qA;
+            out.nq = nq;
+            out.nb = np * nq;
+            out.magic = (65536u + nq - 1) / nq;
+            out.valid = 1;
+            out.gofs = GO_CL ? ((long long)r * PP + gp * PW + qA) * C + c0
+                             : ((long long)r * C + c0) * PP + gp * PW + qA;
+            gp += np;
+            return;
+          }
+        }
+        gci++;
+        gp = 0;
+      }
+    };
+    auto issue = [&](const Item& it, int bf) {
+      const TapS* tp = taps + (long)it.r * nt;
+      if (warp < 4) {   // WX[q][x]: thread = (bin column, pair of tile columns)
+        const int qq = threadIdx.x >> 2, xa = x0 + 2 * (threadIdx.x & 3);
+        float w0 = 0.f, w1 = 0.f;
+        if (qq < it.nq) {
+          const TapS* tq = tp + PH * G + (it.q0 + qq) * G;
+#pragma unroll
+          for (int i = 0; i < (GC ? GC : 1); i++)
+            for (int ii = i; ii < G; ii += (GC ? GC : 1)) {
+              const TapS s = ld_tap(tq + ii);
+              w0 += tap_weight(s, xa);
+              w1 += tap_weight(s, xa + 1);
+            }
+          w0 *= invG;
+          w1 *= invG;
+        }
+        *reinterpret_cast<float4*>(&sm.WX[bf][qq][2 * (threadIdx.x & 3)]) = make_float4(w0, w0, w1, w1);
+      } else {          // WY[y][p]: half-warp = tile row, lane = bin row of the item
+        const int tt = threadIdx.x - 128;
+        const int yy = tt >> 4, pp = tt & 15;
+        float w = 0.f;
+        if (pp < it.np) {
+          const TapS* tq = tp + (it.p0 + pp) * G;
+#pragma unroll
+          for (int i = 0; i < (GC ? GC : 1); i++)
+            for (int ii = i; ii < G; ii += (GC ? GC : 1)) w += tap_weight(ld_tap(tq + ii), y0 + yy);
+          w *= invG;
+        }
+        sm.WY[bf][yy][pp] = make_float2(w, w);
+        const unsigned m = (__ballot_sync(0xffffffffu, w != 0.f) >> (lane & 16)) & 0xffffu;
+        if (pp == 0) sm.prange[bf][yy] = m ? make_int2(__ffs(m) - 1, 31 - __clz(m)) : make_int2(1, 0);
+      }
+      const uint32_t sb = s_base + bf * kBufBytes;
+      const float* gsrc = go + it.gofs;
+      const int nq = it.nq, nb = it.nb;
+      const unsigned magic = it.magic;
+      if (GO_CL) {
+        if (active)
+          for (int pq = warp; pq < nb; pq += 8) {
+            const int pp = (pq * magic) >> 16, qq = pq - pp * nq;
+            cp_async16(sb + (pq * SROW + 4 * lane) * 4, gsrc + (long)(pp * PW + qq) * C + 4 * lane);
+          }
+      } else if (cc == kChunk) {
+        const float* gth = gsrc + cth * PP;
+        const uint32_t sth = sb + cth * 4;
+#pragma unroll 2
+        for (int pq = j; pq < nb; pq += 8) {
+          const int pp = (pq * magic) >> 16, qq = pq - pp * nq;
+          const float* s = gth + (pp * PW + qq);
+          const uint32_t d = sth + pq * (SROW * 4);
+          cp_async4(d, s);
+          cp_async4(d + 128, s + 32 * PP);
+          cp_async4(d + 256, s + 64 * PP);
+          cp_async4(d + 384, s + 96 * PP);
+        }
+      } else {
+        for (int pq = j; pq < nb; pq += 8) {
+          const int pp = (pq * magic) >> 16, qq = pq - pp * nq;
+          const float* s = gsrc + (pp * PW + qq);
+          const uint32_t d = sb + pq * (SROW * 4);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int c = cth + 32 * k;
+            if (c < cc) cp_async4(d + c * 4, s + (long)c * PP);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    auto compute = [&](const Item& it, int bf) {
+      if (y >= H) return;
+      const int2 pr = sm.prange[bf][warp];
+      if (pr.x > pr.y) return;
+      const int nq = it.nq;
+      const u64* wyp = reinterpret_cast<const u64*>(&sm.WY[bf][warp][0]);
+      const float* Sb = sm.S[bf] + 4 * lane + pr.x * nq * SROW;
+      for (int qq = 0; qq < nq; qq++, Sb += SROW) {
+        u64 v0 = 0ull, v1 = 0ull;
+        const float* sp = Sb;
+#pragma unroll 2
+        for (int pp = pr.x; pp <= pr.y; pp++, sp += nq * SROW) {
+          const u64 w2 = wyp[pp];
+          const ulonglong2 f = *reinterpret_cast<const ulonglong2*>(sp);
+          v0 = fma2(w2, f.x, v0);
+          v1 = fma2(w2, f.y, v1);
+        }
+        const ulonglong2* wx = reinterpret_cast<const ulonglong2*>(&sm.WX[bf][qq][0]);
+#pragma unroll
+        for (int k = 0; k < TW / 2; k++) {
+          const ulonglong2 w = wx[k];
+          acc[2 * k][0] = fma2(w.x, v0, acc[2 * k][0]);
+          acc[2 * k][1] = fma2(w.x, v1, acc[2 * k][1]);
+          acc[2 * k + 1][0] = fma2(w.y, v0, acc[2 * k + 1][0]);
+          acc[2 * k + 1][1] = fma2(w.y, v1, acc[2 * k + 1][1]);
+        }
+      }
+    };
+
+    if (threadIdx.x == 0) {
+      generate(sm.ring[0]);
+      generate(sm.ring[1]);
+    }
+    __syncthreads();
+    Item cur = sm.ring[0];
+    int bf = 0;
+    if (cur.valid) issue(cur, 0);
+    for (int i = 0; cur.valid; i++) {
+      cp_async_wait_all();
+      __syncthreads();
+      const Item nxt = sm.ring[(i + 1) & 3];
+      if (threadIdx.x == 0) generate(sm.ring[(i + 2) & 3]);
+      if (nxt.valid) issue(nxt, bf ^ 1);
+      compute(cur, bf);
+      cur = nxt;
+      bf ^= 1;
+    }
+    __syncthreads();
+  }
+
+  // ---- the tile's gradient: written exactly once ----
+  if (active && y < H) {
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
+    const long C4 = C >> 2;
+#pragma unroll
+    for (int x = 0; x < TW; x++)
+      if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
+  }
+}
+
+typedef void (*StagedFn)(PyramidView, TileGrid, const float*, const TapS*, const int4*, int, int, int, int, const int*,
+                         const int*, int);
+
+template <bool GO_CL>
+static StagedFn pick_staged(int PH, int PW, int G) {
+  if (PH == 7 && PW == 7 && G == 2) return bwd_tiles_staged<GO_CL, 7, 2>;
+  if (PH == 14 && PW == 14 && G == 2) return bwd_tiles_staged<GO_CL, 14, 2>;
+  return bwd_tiles_staged<GO_CL, 0, 0>;
+}
+
+}  // namespace bst
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace cpm
@@ -445,6 +763,9 @@ using namespace cpm;
 struct BwdWs {
   size_t seg_count, perm, taps, box, goT, total;
 };
+
+// the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
+static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
 static BwdWs bwd_layout(int64_t K, int L, int B, int C, int PH, int PW, int G) {
   BwdWs w;
@@ -456,7 +777,7 @@ static BwdWs bwd_layout(int64_t K, int L, int B, int C, int PH, int PW, int G) {
   w.perm = take(segs * k * sizeof(int));
   w.taps = take(k * (size_t)(PH + PW) * (size_t)(G > 0 ? G : 1) * sizeof(TapS));
   w.box = take(k * sizeof(int4));
-  w.goT = take(k * (size_t)C * PH * PW * sizeof(float));
+  w.goT = take(bwd_staged_ok(PH, PW, G) ? 0 : k * (size_t)C * PH * PW * sizeof(float));
   w.total = off;
   return w;
 }
@@ -520,14 +841,15 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
     float* goT = (float*)(wsb + w.goT);
     const int Kp = K > 0 ? (int)K : 1;
     const int PP = pooled_h * pooled_w;
+    const bool staged = bwd_staged_ok(pooled_h, pooled_w, sampling_ratio);
     if (K > 0) {
       bwd_bin_rois<<<L * B, 256, 0, st>>>(pv, (const float*)d_rois, (int)K, mp, d_roi_levels, seg_count, perm);
       CPM_CHECK_LAUNCH();
       bwd_roi_taps<<<(unsigned)K, 64, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w, sampling_ratio, aligned,
                                                mp, d_roi_levels, taps, box);
       CPM_CHECK_LAUNCH();
-      // grad_out (K, C, PP) -> (K, PP, C)
-      for (long k0 = 0; k0 < K; k0 += 32768) {
+      // grad_out (K, C, PP) -> (K, PP, C)  (only the unstaged kernel reads the copy)
+      for (long k0 = 0; k0 < K && !staged; k0 += 32768) {
         const int kb = (int)((K - k0) < 32768 ? (K - k0) : 32768);
         dim3 grid((PP + 31) / 32, (C + 31) / 32, kb);
         transpose_go<float><<<grid, 256, 0, st>>>((const float*)d_grad_out + k0 * (long)C * PP, goT + k0 * (long)C * PP, C, PP);
@@ -548,8 +870,15 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
     }
     for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
-    bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, goT, taps, box, Kp, pooled_h, pooled_w,
-                                                                  sampling_ratio, seg_count, perm, chunks);
+    if (staged) {
+      const bst::StagedFn fn = bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
+      CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
+      fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
+          pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
+    } else {
+      bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, goT, taps, box, Kp, pooled_h, pooled_w,
+                                                                    sampling_ratio, seg_count, perm, chunks);
+    }
     CPM_CHECK_LAUNCH();
     return CPM_OK;
   }

@@ -34,6 +34,18 @@ def close(x, ref, rel=1e-5):
         err.max(), bound.flat[err.argmax()], int(bad.sum()), ref.size)
 
 
+def close_sum(x, ref, abs_sum, rel=1e-5):
+    """Backward sums whose terms cancel: the fp32 error of a sum scales with the sum of |terms| (any summation order,
+    the reference's atomicAdd order included), so the bound is rel * (sum|terms| + rms(ref)); abs_sum >= |ref|."""
+    x, ref, abs_sum = (np.asarray(a, dtype=np.float64) for a in (x, ref, abs_sum))
+    assert x.shape == ref.shape == abs_sum.shape
+    rms = float(np.sqrt(np.mean(ref ** 2))) if ref.size else 0.0
+    err = np.abs(x - ref)
+    bad = err > rel * (abs_sum + rms)
+    assert not bad.any(), "max excess %.3e at %d of %d elements" % (
+        (err - rel * (abs_sum + rms)).max(), int(bad.sum()), ref.size)
+
+
 def cuda(a, dtype=None):
     t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
     return t.to(dtype) if dtype is not None else t
@@ -247,6 +259,28 @@ def test_backward_deterministic_and_atomic_modes():
     # K == 0: dense zeros for every level
     z = pooler_backward(go[:0], shapes, SCALES, rois.cuda()[:0], (7, 7), 2, False, 0, m, mode="deterministic")
     assert all(float(t.abs().max()) == 0.0 for t in z)
+
+
+@pytest.mark.parametrize("P,C", [(7, 256), (14, 128), (14, 72)])
+@pytest.mark.parametrize("sr,aligned", [(2, False), (1, False), (2, True)])
+def test_roi_align_backward_staged(P, C, sr, aligned):
+    """The single-pass staged tile kernel (deterministic mode, P * sr <= 32) on every level scale and every RoI size
+    regime (sub-pixel RoIs whose whole bin grid lands in one tile ... RoIs larger than the map), against the oracle
+    (per level, all RoIs) and the red.global.add scatter."""
+    B = 2
+    gen = torch.Generator().manual_seed(300 + P + C + sr)
+    rois = _size_sweep_rois(P * 7 + sr, B)
+    if aligned:
+        rois = rois[(rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])]
+    go = torch.randn(rois.shape[0], C, P, P, generator=gen)
+    for l, (H, W) in ((0, (50, 84)), (2, (13, 21)), (3, (7, 11))):
+        shapes = [(B, C, H, W)]
+        det = pooler_backward(go.cuda(), shapes, [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, mode="deterministic")[0]
+        at = pooler_backward(go.cuda(), shapes, [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, mode="atomic")[0]
+        gref = oracle.roi_align_backward(go.numpy(), rois.numpy(), SCALES[l], P, P, B, C, H, W, sr, aligned)
+        gabs = oracle.roi_align_backward(go.abs().numpy(), rois.numpy(), SCALES[l], P, P, B, C, H, W, sr, aligned)
+        close_sum(det.cpu(), gref, gabs)
+        close_sum(at.cpu(), gref, gabs)
 
 
 def test_level_map_golden(golden):
