@@ -168,11 +168,10 @@ struct TileGrid {
 };
 
 // workspace layout: int32 seg_count[L*B] ; int32 perm[L*B][K]
-__global__ void __launch_bounds__(256) bwd_bin_rois(PyramidView pv, const float* __restrict__ rois, int K, MapperView mp,
-                                                     const int* __restrict__ roi_levels, int* __restrict__ seg_count,
-                                                     int* __restrict__ perm) {
-  __shared__ int wcount[8];
-  const int seg = blockIdx.x;            // seg = level * B + image
+__device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const float* __restrict__ rois, int K, const MapperView& mp,
+                                               const int* __restrict__ roi_levels, int* __restrict__ seg_count,
+                                               int* __restrict__ perm, const int seg) {
+  __shared__ int wcount[8];              // seg = level * B + image
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_warp = ((K + 7) / 8 + 31) & ~31;
   const int beg = warp * per_warp, end = min(K, beg + per_warp);
@@ -234,22 +233,22 @@ struct __align__(16) TapS {
 
 // One CTA per RoI: the RoI's sample taps along both axes (PH*G + PW*G entries) and the pixel box they reach.
 // taps layout: [K][(PH + PW) * G]  (y taps first); box: [K] int4 {ylo, yhi, xlo, xhi}, ylo > yhi when nothing is reached.
-__global__ void __launch_bounds__(64) bwd_roi_taps(PyramidView pv, const float* __restrict__ rois, int K, int PH, int PW, int G,
-                                                    int aligned, MapperView mp, const int* __restrict__ roi_levels,
-                                                    TapS* __restrict__ taps, int4* __restrict__ box) {
-  const int r = blockIdx.x;
+__device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const float* __restrict__ rois, int PH, int PW, int G,
+                                               int aligned, const MapperView& mp, const int* __restrict__ roi_levels,
+                                               TapS* __restrict__ taps, int4* __restrict__ box, const int r, const int tid,
+                                               const int nthr) {
   const float* roi = rois + 5 * (long)r;
   const int l = roi_level_b(roi, pv, mp, roi_levels, r);
   const int nt = (PH + PW) * G;
   TapS* out = taps + (long)r * nt;
   const bool ok = l >= 0 && l < pv.num_levels && (int)roi[0] >= 0 && (int)roi[0] < pv.batch;
   if (!ok) {
-    if (threadIdx.x == 0) box[r] = make_int4(1, 0, 1, 0);
+    if (tid == 0) box[r] = make_int4(1, 0, 1, 0);
     return;
   }
   const int H = pv.H[l], W = pv.W[l];
   const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
-  for (int e = threadIdx.x; e < nt; e += blockDim.x) {
+  for (int e = tid; e < nt; e += nthr) {
     const bool isy = e < PH * G;
     const int k = isy ? e : e - PH * G;
     const int p = k / G, i = k - p * G;
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(64) bwd_roi_taps(PyramidView pv, const float* 
     o.whi = t.whi;
     out[e] = o;
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     // sample coordinates are monotone along an axis, so the first / last sample bound the reached pixels
     const float yf = g.start_h + static_cast<float>(.5f) * g.bin_h / static_cast<float>(G);
     const float yl = g.start_h + (PH - 1) * g.bin_h + static_cast<float>(G - 1 + .5f) * g.bin_h / static_cast<float>(G);
@@ -273,6 +272,21 @@ __global__ void __launch_bounds__(64) bwd_roi_taps(PyramidView pv, const float* 
     const int ylo = yf <= 0.f ? 0 : min((int)yf, H - 1), yhi = yl >= (float)(H - 1) ? H - 1 : (int)fmaxf(yl, 0.f) + 1;
     const int xlo = xf <= 0.f ? 0 : min((int)xf, W - 1), xhi = xl >= (float)(W - 1) ? W - 1 : (int)fmaxf(xl, 0.f) + 1;
     box[r] = none ? make_int4(1, 0, 1, 0) : make_int4(ylo, yhi, xlo, xhi);
+  }
+}
+
+// One launch prepares the whole call: blocks [0, L*B) bin the RoIs by (level, image); every later block builds the
+// tap tables of 4 RoIs (64 threads each).
+__global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* __restrict__ rois, int K, int PH, int PW, int G,
+                                                    int aligned, MapperView mp, const int* __restrict__ roi_levels,
+                                                    int* __restrict__ seg_count, int* __restrict__ perm,
+                                                    TapS* __restrict__ taps, int4* __restrict__ box) {
+  const int nseg = pv.num_levels * pv.batch;
+  if ((int)blockIdx.x < nseg) {
+    bin_rois_block(pv, rois, K, mp, roi_levels, seg_count, perm, blockIdx.x);
+  } else {
+    const int r = 4 * ((int)blockIdx.x - nseg) + (threadIdx.x >> 6);
+    if (r < K) roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, 64);
   }
 }
 
@@ -843,10 +857,9 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
     const int PP = pooled_h * pooled_w;
     const bool staged = bwd_staged_ok(pooled_h, pooled_w, sampling_ratio);
     if (K > 0) {
-      bwd_bin_rois<<<L * B, 256, 0, st>>>(pv, (const float*)d_rois, (int)K, mp, d_roi_levels, seg_count, perm);
-      CPM_CHECK_LAUNCH();
-      bwd_roi_taps<<<(unsigned)K, 64, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w, sampling_ratio, aligned,
-                                               mp, d_roi_levels, taps, box);
+      bwd_prepare<<<(unsigned)(L * B + (K + 3) / 4), 256, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w,
+                                                                    sampling_ratio, aligned, mp, d_roi_levels, seg_count,
+                                                                    perm, taps, box);
       CPM_CHECK_LAUNCH();
       // grad_out (K, C, PP) -> (K, PP, C)  (only the unstaged kernel reads the copy)
       for (long k0 = 0; k0 < K && !staged; k0 += 32768) {
