@@ -135,6 +135,95 @@ __device__ __forceinline__ void run_columns(const char* __restrict__ base, const
   }
 }
 
+// The same loop with the feature loads detached from the arithmetic: every lane streams its 16-byte taps through a private
+// shared-memory ring with cp.async, kRingStages - 1 columns ahead (no register is tied up while a load is in flight and no
+// lane ever reads another lane's slot, so cp.async.wait_group is the only synchronisation).
+template <int NG>
+struct RingCfg {
+  static constexpr int kStages = NG == 1 ? 3 : 2;
+  static constexpr int kRows = NG == 1 ? 4 : 3;             // feature rows per column a slot holds (NR above it: direct loads)
+  static constexpr int kWarpBytes = kStages * kRows * 512;
+};
+
+__device__ __forceinline__ void cp_async16_ca(uint32_t sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NG, int NR, int NW>
+__device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, const unsigned (&rowoff)[4], const u64 (&wy)[4],
+                                                 const Tables<NG>& tb, const int g, float* __restrict__ tptr,
+                                                 ulonglong2* __restrict__ ring /* this lane's first slot */) {
+  constexpr int PP = 49 * NG * NG;
+  constexpr int S = RingCfg<NG>::kStages, NRM = RingCfg<NG>::kRows;
+  const uint32_t ring_s = smem_u32(ring);
+  u64 acc[kBins][2];
+#pragma unroll
+  for (int p = 0; p < kBins; p++) acc[p][0] = acc[p][1] = 0ull;
+  int i = tb.ib[g];
+  int tot = 0;
+#pragma unroll
+  for (int pw = 0; pw < kBins; pw++) tot += tb.cnt[g][pw];
+  const int iend = i + tot;
+  auto issue = [&](int col, int slot) {
+    if (col < iend) {
+      const unsigned xo = (unsigned)tb.xoff[col];
+#pragma unroll
+      for (int k = 0; k < NR; k++) cp_async16_ca(ring_s + (uint32_t)((slot * NRM + k) * 512), base + (size_t)(rowoff[k] + xo));
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < S - 1; st++) issue(i + st, st);
+  int slot = 0, pre = S - 1;             // slot of column i, slot the next issue fills
+#pragma unroll
+  for (int pw = 0; pw < kBins; pw++) {
+    int n = tb.cnt[g][pw];
+#pragma unroll 1
+    for (; n > 0; --n, ++i) {
+      issue(i + S - 1, pre);
+      cp_async_wait<S - 1>();
+      ulonglong2 f[NR];
+#pragma unroll
+      for (int k = 0; k < NR; k++) f[k] = ring[(slot * NRM + k) * 32];
+      u64 vlo = mul2(wy[0], f[0].x), vhi = mul2(wy[0], f[0].y);
+#pragma unroll
+      for (int k = 1; k < NR; k++) {
+        vlo = fma2(wy[k], f[k].x, vlo);
+        vhi = fma2(wy[k], f[k].y, vhi);
+      }
+      const u64* wp = reinterpret_cast<const u64*>(&tb.w[g][i][0]);
+#pragma unroll
+      for (int k = 0; k < NW; k++) {
+        if (pw + k < kBins) {
+          const u64 w = wp[k];
+          acc[pw + k][0] = fma2(w, vlo, acc[pw + k][0]);
+          acc[pw + k][1] = fma2(w, vhi, acc[pw + k][1]);
+        }
+      }
+      slot = slot + 1 == S ? 0 : slot + 1;
+      pre = pre + 1 == S ? 0 : pre + 1;
+    }
+    const float2 a = unpack2(acc[pw][0]), b = unpack2(acc[pw][1]);
+    tptr[pw] = a.x;
+    tptr[PP + pw] = a.y;
+    tptr[2 * PP + pw] = b.x;
+    tptr[3 * PP + pw] = b.y;
+  }
+  cp_async_wait<0>();
+}
+
+template <int NG, int NR>
+__device__ __forceinline__ void run_nw_ring(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
+                                            const int g, float* tptr, ulonglong2* ring) {
+  const int nw = tb.nw[g];
+  if (nw == 2) run_columns_ring<NG, NR, 2>(base, rowoff, wy, tb, g, tptr, ring);
+  else if (nw == 4) run_columns_ring<NG, NR, 4>(base, rowoff, wy, tb, g, tptr, ring);
+  else run_columns_ring<NG, NR, 7>(base, rowoff, wy, tb, g, tptr, ring);
+}
+
 template <int NG, int NR>
 __device__ __forceinline__ void run_nw(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
                                        const int g, float* tptr) {
@@ -168,6 +257,7 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   const RoiGeo<float> geo = roi_geometry<float>(roi, pv.scale[l < 0 || l >= pv.num_levels ? 0 : l], P, P, G, aligned != 0);
   const bool ok = l >= 0 && l < pv.num_levels && geo.b >= 0 && geo.b < pv.batch;
   constexpr int kTileFloats = CH * PP + SK * (CH / 4);
+  constexpr int kTileBytes = (kTileFloats * 4 + 15) & ~15;
   if (!ok) {           // out-of-range level / image index: defined as zeros
     for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
   } else {
@@ -355,8 +445,10 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
     // ---- main loop ----
     const char* base = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C + c0 + 4 * lr);
     float* tptr = tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
-    if (nr == 2) run_nw<NG, 2>(base, rowoff, wy, tb, g, tptr);
-    else if (nr == 3) run_nw<NG, 3>(base, rowoff, wy, tb, g, tptr);
+    ulonglong2* ring = reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(tile) + kTileBytes + warp * RingCfg<NG>::kWarpBytes) + lane;
+    if (nr == 2) run_nw_ring<NG, 2>(base, rowoff, wy, tb, g, tptr, ring);
+    else if (nr == 3) run_nw_ring<NG, 3>(base, rowoff, wy, tb, g, tptr, ring);
+    else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2>(base, rowoff, wy, tb, g, tptr, ring);
     else run_nw<NG, 4>(base, rowoff, wy, tb, g, tptr);
   }
   // ---- tile -> out[n, c0 : c0 + CH, :, :] ----
@@ -399,7 +491,8 @@ int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int
   static thread_local int configured_dev = -1;
   int dev;
   CPM_CHECK_CUDA(cudaGetDevice(&dev));
-  const size_t smem1 = (size_t)128 * 49 * 4, smem2 = (size_t)(64 * 196 + 4 * 16) * 4;
+  const size_t smem1 = (size_t)128 * 49 * 4 + 7 * fwdc::RingCfg<1>::kWarpBytes;
+  const size_t smem2 = (size_t)(64 * 196 + 4 * 16) * 4 + 14 * fwdc::RingCfg<2>::kWarpBytes;
   if (configured_dev != dev) {
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fwdc::roi_align_fwd_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fwdc::roi_align_fwd_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
