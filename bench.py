@@ -26,6 +26,11 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each op's main kernel, from the committed `ncu --set full`
+# capture of this same workload (profiles/ncu_r01_summary.txt); not re-measured by bench.py (a run under ncu is never timed)
+NCU_DRAM_BYTES = {"fwd7": 158.9e6, "fwd14": 322.2e6, "bwd7": 179.1e6, "bwd14": 359.6e6}
+NCU_DRAM_SOURCE = "profiles/ncu_r01_summary.txt (ncu --set full, one capture per kernel)"
+
 METRIC = "roi_align_fwd_bwd_rois_per_sec"
 UNIT = "RoIs/s"
 IMGS_PER_GPU, ROIS_PER_IMG, CHANNELS = 2, 512, 256
@@ -187,7 +192,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     import cpm_r_cnn_b200 as ops
-    from cpm_r_cnn_b200 import _lib, synthetic as sy
+    from cpm_r_cnn_b200 import _lib, sharding, synthetic as sy
     from cpm_r_cnn_b200.roi_align import pooler_backward, pooler_forward
 
     rank = int(os.environ.get("RANK", "0"))
@@ -268,14 +273,10 @@ def run_ours(args):
     sync_all()
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = t_beg.elapsed_time(t_end)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    # whole-job figure: units of all ranks / the slowest rank's device time (cpm_r_cnn_b200/sharding.py)
+    units_total, sec_total, value = sharding.aggregate(K * len(POOLERS) * args.steps, t_beg.elapsed_time(t_end) * 1e-3)
+    ms_step = sec_total * 1e3 / args.steps
     units_per_step = K * len(POOLERS) * world
-    value = units_per_step / (ms_step * 1e-3)
     op_ms = {n: sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i, n in enumerate(names)}
 
     # ---- e2e: host (pinned) buffers in and out, copies inside the timed region ----
@@ -363,10 +364,10 @@ def run_ours(args):
                                  "exceeds the 126 MB L2",
                            "parallelism": "dp%d (images sharded per GPU, no collective inside the ops)" % world},
                 "roofline": {"bound": "hbm", "kernel": {"fwd7": "roi_align_fwd_cols<1> (7x7)", "fwd14": "roi_align_fwd_cols<2> (14x14)",
-                                                         "bwd7": "bwd_tiles (7x7) + its 3 helper launches",
-                                                         "bwd14": "bwd_tiles (14x14) + its 3 helper launches"}[top],
+                                                         "bwd7": "bwd_tiles_staged<0,7,2> (7x7) + bwd_prepare",
+                                                         "bwd14": "bwd_tiles_staged<0,14,2> (14x14) + bwd_prepare"}[top],
                              "achieved": rl_ops[top]["gbs"], "peak": peak, "unit": "GB/s", "frac": rl_ops[top]["frac"],
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": NCU_DRAM_BYTES.get(top), "traffic_source": NCU_DRAM_SOURCE, "peak_source": peak_src,
                              "step": {"bytes": total_bytes, "gbs": total_bytes / (ms_step * 1e-3) / 1e9,
                                       "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
                              "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]}},
@@ -413,7 +414,62 @@ def bench_nms(ops, dev, rank, world, dist, sync_all, iters=10):
             ms = float(t.item())
         res[name] = {"boxes": int(b.shape[0]) * world, "segments": nseg * world, "ms": ms, "kept": int(total.item()),
                      "boxes_per_sec": b.shape[0] * world / (ms * 1e-3)}
+        if rank == 0:
+            res[name]["reference_gpu"] = reference_gpu_nms(name, b, s, seg, nseg, thr, int(total.item()))
+            if res[name]["reference_gpu"].get("ms"):
+                res[name]["speedup_vs_reference_gpu"] = res[name]["reference_gpu"]["ms"] * world / ms if world == 1 else None
     return res
+
+
+def reference_gpu_nms(name, b, s, seg, nseg, thr, kept_ours):
+    """The reference's own single-GPU op path on the same boxes, timed with CUDA events in this process:
+    RPN flavour  = one pet.lib.ops.nms (= torchvision.ops.nms, pet/lib/ops/nms.py:2,10) call per (image, level), the loop
+                   of rpn/inference.py:102-113;
+    detection    = one _C.ml_nms call per image (grid_cascade_rcnn/inference.py:91-97 -> ml_nms.cu:82-146, mask D2H +
+                   host sweep included), from oracle/_ref/pet_ref_cuda.so (the unmodified reference kernel); when that
+                   build is absent, torchvision.ops.batched_nms per image is timed instead and named."""
+    import torchvision
+    out = {}
+    try:
+        order = torch.argsort(seg.to(torch.int64), stable=True)
+        counts = torch.bincount(seg.to(torch.int64), minlength=nseg).tolist()
+        bs, ss = b[order].contiguous(), s[order].contiguous()
+        if name.startswith("rpn"):
+            chunks, pos = [], 0
+            for c in counts:
+                chunks.append((bs[pos:pos + c], ss[pos:pos + c]))
+                pos += c
+            fn = lambda: sum(int(torchvision.ops.nms(bb, sc, thr).numel()) for bb, sc in chunks if bb.shape[0])
+            out["op"] = "torchvision.ops.nms per (image, level)"
+        else:
+            n_cls = 80
+            labels = (seg.to(torch.int64) % n_cls + 1)[order].contiguous()
+            per_img, pos = [], 0
+            for i in range(nseg // n_cls):
+                c = sum(counts[i * n_cls:(i + 1) * n_cls])
+                per_img.append((bs[pos:pos + c], ss[pos:pos + c], labels[pos:pos + c]))
+                pos += c
+            try:
+                from oracle import build_ref
+                ref = build_ref.load("pet_ref_cuda")
+                fn = lambda: sum(int(ref.ml_nms(bb, sc, lb, thr, 0).numel()) for bb, sc, lb in per_img if bb.shape[0])
+                out["op"] = "_C.ml_nms (reference ml_nms.cu, unmodified) per image"
+            except Exception:
+                fn = lambda: sum(int(torchvision.ops.batched_nms(bb, sc, lb, thr).numel()) for bb, sc, lb in per_img if bb.shape[0])
+                out["op"] = "torchvision.ops.batched_nms per image (reference build unavailable)"
+        kept = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out.update({"ms": ms, "boxes_per_sec": b.shape[0] / (ms * 1e-3), "kept": kept, "same_kept_count": kept == kept_ours})
+    except Exception as e:
+        out["unavailable"] = repr(e)[:200]
+    return out
 
 
 def main():
