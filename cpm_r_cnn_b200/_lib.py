@@ -16,6 +16,7 @@ INTERP = {"bilinear": 0, "nearest": 1}
 IOU_PLAIN, IOU_TV_CUDA, IOU_ML_CUDA = 0, 1, 2
 BWD_DETERMINISTIC, BWD_ATOMIC = 0, 1
 FWD_AUTO, FWD_GENERIC, FWD_NHWC, FWD_NHWC_ROWS, FWD_COLS = 0, 1, 2, 3, 4
+POOLED_KCHW, POOLED_KHWC = 0, 1
 ERR_UNSUPPORTED = -2
 
 
@@ -40,6 +41,14 @@ _SIGNATURES = {
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p]),
+    "cpm_roi_align_forward_ex": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "cpm_roi_align_backward_ex": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "cpm_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "cpm_roi_align_backward": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,

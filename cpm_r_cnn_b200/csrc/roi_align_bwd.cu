@@ -805,8 +805,24 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
                                       int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
                                       const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode,
                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+  return cpm_roi_align_backward_ex(grad_feat, d_grad_out, d_rois, K, pooled_h, pooled_w, sampling_ratio, aligned, interpolation,
+                                   mapper, d_roi_levels, mode, CPM_POOLED_KCHW, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
+                                         int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
+                                         const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode,
+                                         int pooled_layout, void* d_workspace, size_t workspace_bytes, void* stream) {
   int rc = check_pyramid(grad_feat, "grad_feat");
   if (rc != CPM_OK) return rc;
+  CPM_CHECK_ARG(pooled_layout == CPM_POOLED_KCHW || pooled_layout == CPM_POOLED_KHWC, "unknown pooled layout %d", pooled_layout);
+  if (pooled_layout == CPM_POOLED_KHWC &&
+      !(mode == CPM_BWD_DETERMINISTIC && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio) && grad_feat->channels % 4 == 0 &&
+        ((uintptr_t)d_grad_out & 15) == 0)) {
+    set_error("a channels-last pooled gradient (CPM_POOLED_KHWC) is read by the deterministic staged kernel only "
+              "(pooled size * sampling_ratio <= 32, C %% 4 == 0, 16-byte aligned grad_out)");
+    return CPM_ERR_UNSUPPORTED;
+  }
   CPM_CHECK_ARG(K >= 0, "K < 0");
   CPM_CHECK_ARG(K < (1L << 30), "K too large");
   CPM_CHECK_ARG(pooled_h >= 1 && pooled_w >= 1, "pooled size must be positive");
@@ -884,7 +900,8 @@ extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void
     for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
     if (staged) {
-      const bst::StagedFn fn = bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
+      const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio)
+                                                                : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
       CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
       fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
           pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);

@@ -595,7 +595,7 @@ static int launch_rows(const PyramidView& pv, const float* rois, long K, int PH,
 int check_device_ptr(const void* p, const char* what);
 bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, int sampling_ratio, const void* d_out);
 int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
-                    const int* lv, float* out, cudaStream_t st);
+                    const int* lv, float* out, int out_channels_last, cudaStream_t st);
 
 int check_pyramid(const cpm_pyramid_t* p, const char* what) {
   CPM_CHECK_ARG(p != nullptr, "%s is NULL", what);
@@ -624,8 +624,16 @@ using namespace cpm;
 extern "C" int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
                                      int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,
                                      const int32_t* d_roi_levels, int impl, void* d_out, void* stream) {
+  return cpm_roi_align_forward_ex(feat, d_rois, K, pooled_h, pooled_w, sampling_ratio, aligned, interpolation, mapper,
+                                  d_roi_levels, impl, CPM_POOLED_KCHW, d_out, stream);
+}
+
+extern "C" int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
+                                        int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,
+                                        const int32_t* d_roi_levels, int impl, int pooled_layout, void* d_out, void* stream) {
   int rc = check_pyramid(feat, "feat");
   if (rc != CPM_OK) return rc;
+  CPM_CHECK_ARG(pooled_layout == CPM_POOLED_KCHW || pooled_layout == CPM_POOLED_KHWC, "unknown pooled layout %d", pooled_layout);
   CPM_CHECK_ARG(K >= 0, "K < 0");
   CPM_CHECK_ARG(pooled_h >= 1 && pooled_w >= 1, "pooled size must be positive");
   CPM_CHECK_ARG(interpolation == CPM_INTERP_BILINEAR || interpolation == CPM_INTERP_NEAREST,
@@ -655,7 +663,13 @@ extern "C" int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_ro
     return CPM_ERR_UNSUPPORTED;
   }
   if (cols_ok && (impl == CPM_FWD_AUTO || impl == CPM_FWD_COLS))
-    return launch_fwd_cols(pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, (float*)d_out, st);
+    return launch_fwd_cols(pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, (float*)d_out,
+                           pooled_layout == CPM_POOLED_KHWC, st);
+  if (pooled_layout == CPM_POOLED_KHWC) {
+    set_error("a channels-last pooled output (CPM_POOLED_KHWC) is produced by the column-table kernel only: NHWC fp32 pyramid, "
+              "bilinear, 7x7 or 14x14 pooler, sampling_ratio 1 or 2, C %% 128 == 0 (7x7) / C %% 64 == 0 (14x14)");
+    return CPM_ERR_UNSUPPORTED;
+  }
   if ((impl == CPM_FWD_NHWC || impl == CPM_FWD_NHWC_ROWS) && !nhwc_ok) {
     set_error("CPM_FWD_NHWC needs an NHWC fp32 pyramid, bilinear interpolation, C %% 4 == 0 and 16-byte aligned maps");
     return CPM_ERR_UNSUPPORTED;

@@ -94,9 +94,26 @@ struct Tables {
 };
 
 // One warp's share: NR feature rows per lane, NW bins per column.
-template <int NG, int NR, int NW>
+// OCL: the pooled output is channels-last (K, PH, PW, C): a finished bin is one 16-byte store per lane straight to global
+// memory (tptr points at the lane's 4 channels of the group's first bin, ostride = C); otherwise it goes to the
+// (channel, bin)-ordered shared-memory tile.
+template <int NG, bool OCL>
+__device__ __forceinline__ void store_bin(float* __restrict__ tptr, int pw, int ostride, u64 lo, u64 hi) {
+  constexpr int PP = 49 * NG * NG;
+  const float2 a = unpack2(lo), b = unpack2(hi);
+  if (OCL) {
+    *reinterpret_cast<float4*>(tptr + (size_t)pw * ostride) = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    tptr[pw] = a.x;
+    tptr[PP + pw] = a.y;
+    tptr[2 * PP + pw] = b.x;
+    tptr[3 * PP + pw] = b.y;
+  }
+}
+
+template <int NG, int NR, int NW, bool OCL>
 __device__ __forceinline__ void run_columns(const char* __restrict__ base, const unsigned (&rowoff)[4], const u64 (&wy)[4],
-                                            const Tables<NG>& tb, const int g, float* __restrict__ tptr) {
+                                            const Tables<NG>& tb, const int g, float* __restrict__ tptr, const int ostride) {
   constexpr int PP = 49 * NG * NG;
   u64 acc[kBins][2];
 #pragma unroll
@@ -127,11 +144,7 @@ __device__ __forceinline__ void run_columns(const char* __restrict__ base, const
         }
       }
     }
-    const float2 a = unpack2(acc[pw][0]), b = unpack2(acc[pw][1]);
-    tptr[pw] = a.x;
-    tptr[PP + pw] = a.y;
-    tptr[2 * PP + pw] = b.x;
-    tptr[3 * PP + pw] = b.y;
+    store_bin<NG, OCL>(tptr, pw, ostride, acc[pw][0], acc[pw][1]);
   }
 }
 
@@ -152,9 +165,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NG, int NR, int NW>
+template <int NG, int NR, int NW, bool OCL>
 __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, const unsigned (&rowoff)[4], const u64 (&wy)[4],
-                                                 const Tables<NG>& tb, const int g, float* __restrict__ tptr,
+                                                 const Tables<NG>& tb, const int g, float* __restrict__ tptr, const int ostride,
                                                  ulonglong2* __restrict__ ring /* this lane's first slot */) {
   constexpr int PP = 49 * NG * NG;
   constexpr int S = RingCfg<NG>::kStages, NRM = RingCfg<NG>::kRows;
@@ -206,36 +219,32 @@ __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, 
       slot = slot + 1 == S ? 0 : slot + 1;
       pre = pre + 1 == S ? 0 : pre + 1;
     }
-    const float2 a = unpack2(acc[pw][0]), b = unpack2(acc[pw][1]);
-    tptr[pw] = a.x;
-    tptr[PP + pw] = a.y;
-    tptr[2 * PP + pw] = b.x;
-    tptr[3 * PP + pw] = b.y;
+    store_bin<NG, OCL>(tptr, pw, ostride, acc[pw][0], acc[pw][1]);
   }
   cp_async_wait<0>();
 }
 
-template <int NG, int NR>
+template <int NG, int NR, bool OCL>
 __device__ __forceinline__ void run_nw_ring(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
-                                            const int g, float* tptr, ulonglong2* ring) {
+                                            const int g, float* tptr, const int ostride, ulonglong2* ring) {
   const int nw = tb.nw[g];
-  if (nw == 2) run_columns_ring<NG, NR, 2>(base, rowoff, wy, tb, g, tptr, ring);
-  else if (nw == 4) run_columns_ring<NG, NR, 4>(base, rowoff, wy, tb, g, tptr, ring);
-  else run_columns_ring<NG, NR, 7>(base, rowoff, wy, tb, g, tptr, ring);
+  if (nw == 2) run_columns_ring<NG, NR, 2, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
+  else if (nw == 4) run_columns_ring<NG, NR, 4, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
+  else run_columns_ring<NG, NR, 7, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
 }
 
-template <int NG, int NR>
+template <int NG, int NR, bool OCL>
 __device__ __forceinline__ void run_nw(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
-                                       const int g, float* tptr) {
+                                       const int g, float* tptr, const int ostride) {
   const int nw = tb.nw[g];
-  if (nw == 2) run_columns<NG, NR, 2>(base, rowoff, wy, tb, g, tptr);
-  else if (nw == 4) run_columns<NG, NR, 4>(base, rowoff, wy, tb, g, tptr);
-  else run_columns<NG, NR, 7>(base, rowoff, wy, tb, g, tptr);
+  if (nw == 2) run_columns<NG, NR, 2, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
+  else if (nw == 4) run_columns<NG, NR, 4, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
+  else run_columns<NG, NR, 7, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
 }
 
 // NG = 1: 7x7 pooler, CTA = 7 warps (one bin row each) x 128 channels.
 // NG = 2: 14x14 pooler, CTA = 14 warps (7 row pairs x 2 column groups) x 64 channels; half-warps own different bin rows.
-template <int NG>
+template <int NG, bool OCL>
 __global__ void __launch_bounds__(224 * NG, NG == 1 ? 3 : 2)
 roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int aligned, MapperView mp,
                    const int* __restrict__ roi_levels, float* __restrict__ out, int chunks) {
@@ -256,10 +265,15 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   if (pv.num_levels > 1) l = roi_levels ? roi_levels[n] : fpn_level(roi[1], roi[2], roi[3], roi[4], mp);
   const RoiGeo<float> geo = roi_geometry<float>(roi, pv.scale[l < 0 || l >= pv.num_levels ? 0 : l], P, P, G, aligned != 0);
   const bool ok = l >= 0 && l < pv.num_levels && geo.b >= 0 && geo.b < pv.batch;
-  constexpr int kTileFloats = CH * PP + SK * (CH / 4);
+  constexpr int kTileFloats = OCL ? 0 : CH * PP + SK * (CH / 4);      // a channels-last output needs no staging tile
   constexpr int kTileBytes = (kTileFloats * 4 + 15) & ~15;
   if (!ok) {           // out-of-range level / image index: defined as zeros
-    for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
+    if (OCL) {
+      for (int e = threadIdx.x; e < PP * (CH / 4); e += blockDim.x)
+        *reinterpret_cast<float4*>(out + ((size_t)n * PP + e / (CH / 4)) * C + c0 + 4 * (e % (CH / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
+    }
   } else {
     const int H = pv.H[l], W = pv.W[l];
     const int NS = P * G;                  // samples per axis (<= 28)
@@ -444,13 +458,15 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
     __syncthreads();
     // ---- main loop ----
     const char* base = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C + c0 + 4 * lr);
-    float* tptr = tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
+    float* tptr = OCL ? out + ((size_t)n * PP + ph * P + kBins * g) * C + c0 + 4 * lr
+                      : tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
     ulonglong2* ring = reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(tile) + kTileBytes + warp * RingCfg<NG>::kWarpBytes) + lane;
-    if (nr == 2) run_nw_ring<NG, 2>(base, rowoff, wy, tb, g, tptr, ring);
-    else if (nr == 3) run_nw_ring<NG, 3>(base, rowoff, wy, tb, g, tptr, ring);
-    else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2>(base, rowoff, wy, tb, g, tptr, ring);
-    else run_nw<NG, 4>(base, rowoff, wy, tb, g, tptr);
+    if (nr == 2) run_nw_ring<NG, 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+    else if (nr == 3) run_nw_ring<NG, 3, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+    else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+    else run_nw<NG, 4, OCL>(base, rowoff, wy, tb, g, tptr, C);
   }
+  if (OCL) return;
   // ---- tile -> out[n, c0 : c0 + CH, :, :] ----
   fence_async_smem();
   __syncthreads();
@@ -487,25 +503,22 @@ bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
 }
 
 int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
-                    const int* lv, float* out, cudaStream_t st) {
-  static thread_local int configured_dev = -1;
-  int dev;
-  CPM_CHECK_CUDA(cudaGetDevice(&dev));
-  const size_t smem1 = (size_t)128 * 49 * 4 + 7 * fwdc::RingCfg<1>::kWarpBytes;
-  const size_t smem2 = (size_t)(64 * 196 + 4 * 16) * 4 + 14 * fwdc::RingCfg<2>::kWarpBytes;
-  if (configured_dev != dev) {
-    CPM_CHECK_CUDA(cudaFuncSetAttribute(fwdc::roi_align_fwd_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    CPM_CHECK_CUDA(cudaFuncSetAttribute(fwdc::roi_align_fwd_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    configured_dev = dev;
-  }
+                    const int* lv, float* out, int out_channels_last, cudaStream_t st) {
+  const size_t ring1 = 7 * fwdc::RingCfg<1>::kWarpBytes, ring2 = 14 * fwdc::RingCfg<2>::kWarpBytes;
+  const size_t smem1 = (out_channels_last ? 0 : (size_t)128 * 49 * 4) + ring1;
+  const size_t smem2 = (out_channels_last ? 0 : (size_t)(64 * 196 + 4 * 16) * 4) + ring2;
   if (P == 7) {
     const int chunks = pv.channels / 128;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
-    fwdc::roi_align_fwd_cols<1><<<(unsigned)(K * chunks), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
+    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<1, true> : fwdc::roi_align_fwd_cols<1, false>;
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    fn<<<(unsigned)(K * chunks), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
   } else {
     const int chunks = pv.channels / 64;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
-    fwdc::roi_align_fwd_cols<2><<<(unsigned)(K * chunks), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
+    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<2, true> : fwdc::roi_align_fwd_cols<2, false>;
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    fn<<<(unsigned)(K * chunks), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
   }
   CPM_CHECK_LAUNCH();
   return CPM_OK;

@@ -56,14 +56,15 @@ class _PyramidROIAlign(Function):
         ctx.save_for_backward(rois)
         ctx.cfg = cfg
         ctx.shapes = [tuple(t.shape) for t in levels]
-        output_size, scales, sampling_ratio, aligned, interp, mapper = cfg
-        return pooler_forward(list(levels), scales, rois, output_size, sampling_ratio, aligned, interp, mapper)
+        output_size, scales, sampling_ratio, aligned, interp, mapper, channels_last = cfg
+        return pooler_forward(list(levels), scales, rois, output_size, sampling_ratio, aligned, interp, mapper,
+                              channels_last=channels_last)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
         rois, = ctx.saved_tensors
-        output_size, scales, sampling_ratio, aligned, interp, mapper = ctx.cfg
+        output_size, scales, sampling_ratio, aligned, interp, mapper, _ = ctx.cfg
         grads = pooler_backward(grad_output, ctx.shapes, scales, rois, output_size, sampling_ratio, aligned, interp,
                                 mapper)
         return (None, None) + tuple(grads)
@@ -90,6 +91,9 @@ class Pooler(nn.Module):
         lvl_min = -torch.log2(torch.tensor(scales[0], dtype=torch.float32)).item()
         lvl_max = -torch.log2(torch.tensor(scales[-1], dtype=torch.float32)).item()
         self.map_levels = LevelMapper(lvl_min, lvl_max)
+        # Extension (not in the reference): set to torch.channels_last for heads whose convolutions run in channels_last
+        # (the 14x14 grid head); the pooled tensor then has channels_last strides and its gradient is read in place.
+        self.pooled_memory_format = torch.contiguous_format
 
     def convert_to_roi_format(self, boxes):
         """poolers.py:90-101: (K,5) [image index, x1, y1, x2, y2] in the boxes' dtype."""
@@ -105,9 +109,11 @@ class Pooler(nn.Module):
         num_levels = len(self.poolers)
         rois = self.convert_to_roi_format(boxes)
         if num_levels == 1:
+            self.poolers[0].pooled_memory_format = self.pooled_memory_format
             return self.poolers[0](x[0], rois)
         levels = [_float_function(t) for t in list(x)[:num_levels]]
         rois = _float_function(rois).to(levels[0].dtype)
         cfg = (self.output_size, self.scales[:len(levels)], self.sampling_ratio, self.aligned,
-               INTERPOLATION_METHOD[self.interpolation], self.map_levels.c_struct())
+               INTERPOLATION_METHOD[self.interpolation], self.map_levels.c_struct(),
+               self.pooled_memory_format == torch.channels_last)
         return _PyramidROIAlign.apply(rois, cfg, *levels)

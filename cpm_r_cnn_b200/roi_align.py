@@ -64,8 +64,12 @@ def _prepare_levels(levels, interpolation):
     return [t.contiguous() for t in levels], _lib.NCHW
 
 
-def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper, impl=_lib.FWD_AUTO):
-    """One launch for the whole pyramid: list[(B,C,H_l,W_l)] + (K,5) rois -> (K,C,PH,PW)."""
+def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper, impl=_lib.FWD_AUTO,
+                   channels_last=False):
+    """One launch for the whole pyramid: list[(B,C,H_l,W_l)] + (K,5) rois -> (K,C,PH,PW).
+
+    channels_last=True returns the same logical tensor with torch.channels_last strides (memory (K,PH,PW,C)): what a
+    channels_last conv head consumes directly; the kernel then stores channel vectors straight from registers."""
     for t in levels:
         _lib.require_cuda(t, "input")
     _lib.require_cuda(rois, "rois")
@@ -78,17 +82,27 @@ def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, i
         raise RuntimeError("cpm_ops: roi_align supports float32 and float64 inputs (got %s)" % x0.dtype)
     ph, pw = output_size
     K, C = rois.shape[0], x0.shape[1]
-    out = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device)
+    out = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device,
+                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     if K == 0:
         return out
     staged, layout = _prepare_levels(levels, interpolation)
     pyr = make_pyramid(staged, scales, layout)
     rois = rois.contiguous()
+    args = (ctypes.byref(pyr), _lib.ptr(rois), K, ph, pw, int(sampling_ratio), int(bool(aligned)), interpolation,
+            ctypes.byref(mapper) if mapper is not None else None, None, impl)
     with _lib.device_of(x0):
-        _lib.check(_lib.lib().cpm_roi_align_forward(ctypes.byref(pyr), _lib.ptr(rois), K, ph, pw, int(sampling_ratio),
-                                                    int(bool(aligned)), interpolation,
-                                                    ctypes.byref(mapper) if mapper is not None else None, None, impl,
-                                                    _lib.ptr(out), _lib.stream_ptr(x0.device)))
+        L = _lib.lib()
+        if channels_last:
+            rc = L.cpm_roi_align_forward_ex(*args, _lib.POOLED_KHWC, _lib.ptr(out), _lib.stream_ptr(x0.device))
+            if rc == _lib.ERR_UNSUPPORTED:
+                # parameters outside the column-table kernel: pool into the reference layout, let torch restride
+                tmp = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device)
+                _lib.check(L.cpm_roi_align_forward_ex(*args, _lib.POOLED_KCHW, _lib.ptr(tmp), _lib.stream_ptr(x0.device)))
+                return tmp.contiguous(memory_format=torch.channels_last)
+            _lib.check(rc)
+        else:
+            _lib.check(L.cpm_roi_align_forward_ex(*args, _lib.POOLED_KCHW, _lib.ptr(out), _lib.stream_ptr(x0.device)))
     return out
 
 
@@ -107,24 +121,33 @@ def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_rat
     if B == 0 or any(g.numel() == 0 for g in grads):
         return grads
     pyr = make_pyramid(grads, scales, _lib.NHWC if nhwc else _lib.NCHW)
-    grad_output = grad_output.contiguous()
     rois = rois.contiguous()
     det_ok = nhwc and sampling_ratio >= 1 and ph <= 32 and pw <= 32
     use = _lib.BWD_DETERMINISTIC if (mode == "deterministic" and det_ok) else _lib.BWD_ATOMIC
+    # a channels_last-strided pooled gradient (what a channels_last conv head hands back) is read in place by the staged
+    # kernel; anything else is taken in the reference's (K,C,PH,PW) order
+    staged = use == _lib.BWD_DETERMINISTIC and ph * sampling_ratio <= 32 and pw * sampling_ratio <= 32
+    khwc = (staged and K > 0 and ph * pw > 1 and C > 1 and not grad_output.is_contiguous()
+            and grad_output.is_contiguous(memory_format=torch.channels_last) and grad_output.data_ptr() % 16 == 0)
+    if not khwc:
+        grad_output = grad_output.contiguous()
+    layout = _lib.POOLED_KHWC if khwc else _lib.POOLED_KCHW
     ws, ws_bytes = None, 0
     with _lib.device_of(grad_output):
         if use == _lib.BWD_DETERMINISTIC:
             ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes(K, len(shapes), B, C, ph, pw, int(sampling_ratio)))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        _lib.check(_lib.lib().cpm_roi_align_backward(ctypes.byref(pyr), _lib.ptr(grad_output), _lib.ptr(rois), K, ph, pw,
-                                                     int(sampling_ratio), int(bool(aligned)), interpolation,
-                                                     ctypes.byref(mapper) if mapper is not None else None, None, use,
-                                                     _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+        _lib.check(_lib.lib().cpm_roi_align_backward_ex(ctypes.byref(pyr), _lib.ptr(grad_output), _lib.ptr(rois), K, ph, pw,
+                                                        int(sampling_ratio), int(bool(aligned)), interpolation,
+                                                        ctypes.byref(mapper) if mapper is not None else None, None, use,
+                                                        layout, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
     return grads
 
 
 class _ROIAlign(Function):
     """pet/lib/ops/roi_align.py:14-60 (same argument list, same `(grad_input, None x 6)` backward)."""
+
+    pooled_channels_last = False     # set by ROIAlign.forward around the call (the Function keeps the reference signature)
 
     @staticmethod
     def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio, aligned, interpolation="bilinear"):
@@ -136,7 +159,7 @@ class _ROIAlign(Function):
         ctx.aligned = aligned
         ctx.interpolation_method = INTERPOLATION_METHOD[interpolation]
         return pooler_forward([input], [spatial_scale], roi, ctx.output_size, sampling_ratio, aligned,
-                              ctx.interpolation_method, None)
+                              ctx.interpolation_method, None, channels_last=_ROIAlign.pooled_channels_last)
 
     @staticmethod
     @once_differentiable
@@ -166,12 +189,20 @@ class ROIAlign(nn.Module):
         self.sampling_ratio = sampling_ratio
         self.aligned = aligned
         self.interpolation_method = interpolation
+        # Extension (not in the reference): torch.channels_last makes forward return the pooled tensor with channels_last
+        # strides -- for heads that run their convolutions in channels_last.  The default is the reference's layout
+        # (heads that flatten with x.view(K, -1), cls_heads.py:43, need it).
+        self.pooled_memory_format = torch.contiguous_format
 
     def forward(self, input, rois):
         """input: NCHW images (any strides); rois: Bx5 boxes, first column = index into N, then xyxy."""
         assert rois.dim() == 2 and rois.size(1) == 5
-        return roi_align(_float_function(input), _float_function(rois), self.output_size, self.spatial_scale,
-                         self.sampling_ratio, self.aligned, self.interpolation_method)
+        _ROIAlign.pooled_channels_last = self.pooled_memory_format == torch.channels_last
+        try:
+            return roi_align(_float_function(input), _float_function(rois), self.output_size, self.spatial_scale,
+                             self.sampling_ratio, self.aligned, self.interpolation_method)
+        finally:
+            _ROIAlign.pooled_channels_last = False
 
     def __repr__(self):
         tmpstr = self.__class__.__name__ + "("

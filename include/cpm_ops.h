@@ -126,13 +126,29 @@ CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois,
  * reaches -- the reference's at::zeros + atomicAdd, :451-452,:340-347), also when K == 0.
  *   mode        CPM_BWD_DETERMINISTIC (needs the workspace) | CPM_BWD_ATOMIC
  * Workspace (deterministic mode): cpm_roi_align_backward_workspace_bytes(...) bytes, 256-byte aligned; it holds the
- * per-(level,image) RoI lists, the per-RoI tap tables and the channel-vector copy (K, PH*PW, C) of grad_out. */
+ * per-(level,image) RoI lists and the per-RoI tap tables (and, only for poolers with pooled size * sampling_ratio > 32,
+ * which the single-pass staged kernel does not take, a channel-vector copy (K, PH*PW, C) of grad_out). */
 CPM_API size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
                                                       int pooled_w, int sampling_ratio);
 CPM_API int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
                            int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
                            const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode,
                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Memory layout of the POOLED tensor (forward output / backward grad_out).  The reference always produces
+ * (K, C, PH, PW) contiguous (ROIAlign_cuda.cu:390-391); a head that runs in torch.channels_last (the conv stack of the
+ * 14x14 grid head, grid_cascade_rcnn heads) exchanges the same logical tensor as (K, PH, PW, C), which saves both
+ * kernels the (channel, bin) <-> channel-vector transposition.  The _ex entry points take the layout; the plain ones
+ * above are the KCHW case.  KHWC is served by the fast kernels only (CPM_ERR_UNSUPPORTED otherwise: the caller converts). */
+#define CPM_POOLED_KCHW 0
+#define CPM_POOLED_KHWC 1
+CPM_API int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
+                             int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,
+                             const int32_t* d_roi_levels, int impl, int pooled_layout, void* d_out, void* stream);
+CPM_API int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
+                              int pooled_h, int pooled_w, int sampling_ratio, int aligned, int interpolation,
+                              const cpm_level_mapper_t* mapper, const int32_t* d_roi_levels, int mode, int pooled_layout,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* LevelMapper alone (poolers.py:29-40): d_levels int64[K]. */
 CPM_API int cpm_level_map(const float* d_rois, int64_t K, const cpm_level_mapper_t* mapper, int64_t* d_levels, void* stream);

@@ -486,3 +486,40 @@ def test_live_reference_cuda_ml_nms():
         want = ref.ml_nms(b, s, lab, thr, topk)
         got = ops.ml_nms(b, s, lab, thr, topk)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("P,C", [(7, 128), (14, 64), (14, 256)])
+def test_pooled_channels_last_matches_contiguous(P, C):
+    """Extension: a channels_last pooled tensor (memory (K,PH,PW,C)) out of the forward and into the backward gives
+    bit-identical values to the reference (K,C,PH,PW) layout -- same arithmetic, different addressing."""
+    B = 2
+    gen = torch.Generator().manual_seed(900 + P + C)
+    feats = synthetic.pyramid(gen, B, C, 200, 336)
+    rois = torch.cat([synthetic.coco_like_rois(gen, 40, B, 200, 336), _size_sweep_rois(3, B)], 0).cuda()
+    xs = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    m = _lib.make_mapper(2, 5)
+    a = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m)
+    b = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m, channels_last=True)
+    assert a.is_contiguous() and b.is_contiguous(memory_format=torch.channels_last) and not b.is_contiguous()
+    assert torch.equal(a, b)
+    go = torch.randn(a.shape, generator=gen).cuda()
+    shapes = [tuple(f.shape) for f in feats]
+    ga = pooler_backward(go, shapes, SCALES, rois, (P, P), 2, False, 0, m)
+    gb = pooler_backward(go.contiguous(memory_format=torch.channels_last), shapes, SCALES, rois, (P, P), 2, False, 0, m)
+    for x, y in zip(ga, gb):
+        assert torch.equal(x, y)
+    # through the modules + autograd, with a channels_last consumer
+    pooler = ops.Pooler("ROIAlign", (P, P), SCALES, 2)
+    pooler.pooled_memory_format = torch.channels_last
+    boxlists = [ops.BoxList(rois[rois[:, 0] == i][:, 1:], (336, 200)) for i in range(B)]
+    order = torch.cat([torch.nonzero(rois[:, 0] == i).squeeze(1) for i in range(B)])
+    xg = [x.detach().requires_grad_(True) for x in xs]
+    out = pooler(xg, boxlists)
+    assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, a[order])
+    w = torch.randn(8, C, 3, 3, generator=gen).cuda().contiguous(memory_format=torch.channels_last)
+    torch.nn.functional.conv2d(out, w, padding=1).square().mean().backward()
+    assert all(x.grad is not None and torch.isfinite(x.grad).all() for x in xg)
+    # unsupported parameters fall back to pooling in the reference layout + a torch restride
+    odd = pooler_forward(xs, SCALES, rois, (5, 3), 2, False, 0, m, channels_last=True)
+    assert odd.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(odd, pooler_forward(xs, SCALES, rois, (5, 3), 2, False, 0, m))

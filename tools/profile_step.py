@@ -20,19 +20,22 @@ ap.add_argument("--nms", action="store_true")
 ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (no host enqueue cost in the numbers)")
 ap.add_argument("--mode", default="deterministic")
 ap.add_argument("--impl", type=int, default=0)
+ap.add_argument("--cl", action="store_true", help="channels_last pooled tensors (forward output and grad_out)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 rois_h, feats_h, gouts_h = bench.make_workload(0)
 feats = [f.to(dev).contiguous(memory_format=torch.channels_last) for f in feats_h]
 rois = rois_h.to(dev)
 gouts = [g.to(dev) for g in gouts_h]
+if args.cl:
+    gouts = [g.contiguous(memory_format=torch.channels_last) for g in gouts]
 shapes = [tuple(f.shape) for f in feats_h]
 mapper = _lib.make_mapper(2, 5)
 tot = {}
 if args.graph:
     ops_ = []
     for p, go in zip(bench.POOLERS, gouts):
-        ops_.append(lambda p=p: pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl))
+        ops_.append(lambda p=p: pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl, channels_last=args.cl))
         ops_.append(lambda p=p, go=go: pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode))
     for f in ops_:
         f(); f()
@@ -58,7 +61,7 @@ for i in range(args.steps):
     k = 0
     for p, go in zip(bench.POOLERS, gouts):
         evs[k].record()
-        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl)
+        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl, channels_last=args.cl)
         evs[k + 1].record()
         grads = pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode)
         k += 2
