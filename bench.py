@@ -203,6 +203,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
@@ -278,6 +280,44 @@ def run_ours(args):
     ms_step = sec_total * 1e3 / args.steps
     units_per_step = K * len(POOLERS) * world
     op_ms = {n: sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i, n in enumerate(names)}
+
+    # ---- the same four ops with channels_last pooled tensors (extension, not part of `value`): the forward returns the
+    #      pooled block with channels_last strides and the backward reads a channels_last gradient in place ----
+    cl_ms = {}
+    try:
+        gouts_cl = [g.contiguous(memory_format=torch.channels_last) for g in gouts]
+        cl_fns = []
+        for p, go in zip(POOLERS, gouts_cl):
+            cl_fns += [(lambda p=p: pooler_forward(feats, scales, rois, p, SAMPLING, False, 0, mapper, channels_last=True)),
+                       op_bwd(p, go)]
+        with torch.cuda.stream(side):
+            for fn in cl_fns:
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        sync_all()
+        cl_graphs, cl_keep = [], []
+        for fn in cl_fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cl_keep.append(fn())
+            cl_graphs.append(g)
+        n_cl = max(3, min(args.steps, 20))
+        acc = [0.0] * 4
+        for it in range(n_cl + 2):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            for j, g in enumerate(cl_graphs):
+                e[j].record()
+                g.replay()
+            e[4].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                for j in range(4):
+                    acc[j] += e[j].elapsed_time(e[j + 1])
+        cl_ms = {n: acc[j] / n_cl for j, n in enumerate(names)}
+        del cl_graphs, cl_keep, gouts_cl
+    except Exception as ex:      # reported, never fatal for the headline
+        cl_ms = {"error": repr(ex)[:200]}
+    sync_all()
 
     # ---- e2e: host (pinned) buffers in and out, copies inside the timed region ----
     # One step = H2D of the pyramid, the RoIs and both pooled gradients, the two Pooler modules forward + one autograd
@@ -370,7 +410,10 @@ def run_ours(args):
                              "traffic": NCU_DRAM_BYTES.get(top), "traffic_source": NCU_DRAM_SOURCE, "peak_source": peak_src,
                              "step": {"bytes": total_bytes, "gbs": total_bytes / (ms_step * 1e-3) / 1e9,
                                       "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
-                             "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]}},
+                             "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]},
+                             "ops_channels_last_pooled": ({n: {"ms": cl_ms[n], "gbs": ab[n] / (cl_ms[n] * 1e-3) / 1e9,
+                                                               "frac": ab[n] / (cl_ms[n] * 1e-3) / 1e9 / peak} for n in names}
+                                                          if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks, "nms": nms}

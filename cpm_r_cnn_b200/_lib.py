@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpm_ops.so")
+LIB_PATH = os.environ.get("CPM_OPS_LIB") or os.path.join(_HERE, "libcpm_ops.so")
 
 CPM_MAX_LEVELS = 8
 F32, F64, BF16 = 0, 1, 2

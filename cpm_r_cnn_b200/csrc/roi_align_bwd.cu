@@ -469,6 +469,7 @@ namespace bst {
 
 constexpr int NBUF = 56;               // bins per staging buffer (4 bin rows of a 14-wide pooler)
 constexpr int SROW = kChunk + 4;       // floats per staged bin (528 B: rows stay 16-byte aligned, 4-byte stores conflict-free)
+constexpr int kRound = 2 * kTileThreads;   // RoIs of the (level, image) list scanned per round
 constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the tables hold (the path needs P * G <= 32)
 
 struct __align__(16) Item {
@@ -485,8 +486,8 @@ struct Smem {
   float2 WY[2][TH][MAXP];
   int2 prange[2][TH];                  // first / last bin row of the item with weight on the tile row
   Item ring[4];
-  int cand[kTileThreads];
-  int crange[kTileThreads];            // pA | pB << 8 | qA << 16 | qB << 24, or -1
+  int cand[kRound];
+  int crange[kRound];                  // pA | pB << 8 | qA << 16 | qB << 24, or -1
   int wsum[8];
 };
 
@@ -546,24 +547,30 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
   const uint32_t s_base = smem_u32(&sm.S[0][0]);
   constexpr uint32_t kBufBytes = NBUF * SROW * 4;
 
-  for (int base = 0; base < nseg; base += kTileThreads) {
-    // ---- RoIs of this (level, image) whose reach intersects the tile, in RoI order ----
-    bool hit = false;
-    int me = -1;
-    if (base + threadIdx.x < nseg) {
-      me = plist[base + threadIdx.x];
-      const int4 bx = __ldg(box + me);
-      hit = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
+  for (int base = 0; base < nseg; base += kRound) {
+    // ---- RoIs of this (level, image) whose reach intersects the tile, in RoI order (two list entries per thread) ----
+    bool hit[2] = {false, false};
+    int me[2] = {-1, -1};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = base + 2 * threadIdx.x + e;
+      if (i < nseg) {
+        me[e] = plist[i];
+        const int4 bx = __ldg(box + me[e]);
+        hit[e] = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
+      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) sm.wsum[warp] = __popc(bal);
+    const unsigned bal0 = __ballot_sync(0xffffffffu, hit[0]), bal1 = __ballot_sync(0xffffffffu, hit[1]);
+    if (lane == 0) sm.wsum[warp] = __popc(bal0) + __popc(bal1);
     __syncthreads();
-    int pos = __popc(bal & ((1u << lane) - 1)), ncand = 0;
+    const unsigned below = (1u << lane) - 1;
+    int pos = __popc(bal0 & below) + __popc(bal1 & below), ncand = 0;
     for (int w = 0; w < 8; w++) {
       if (w < warp) pos += sm.wsum[w];
       ncand += sm.wsum[w];
     }
-    if (hit) sm.cand[pos] = me;
+    if (hit[0]) sm.cand[pos] = me[0];
+    if (hit[1]) sm.cand[pos + (hit[0] ? 1 : 0)] = me[1];
     __syncthreads();
     if (ncand == 0) continue;            // (uniform) nothing reaches the tile in this round
     // ---- per candidate: the bin rows / columns with a sample tap inside the tile (lane = sample) ----
