@@ -380,6 +380,7 @@ def run_ours(args):
 
     # ---- NMS half of the metric (configs[2]) ----
     nms = bench_nms(ops, dev, rank, world, dist, sync_all)
+    decode = bench_decode(ops, dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -416,7 +417,7 @@ def run_ours(args):
                                                           if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms}
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -461,6 +462,35 @@ def bench_nms(ops, dev, rank, world, dist, sync_all, iters=10):
             res[name]["reference_gpu"] = reference_gpu_nms(name, b, s, seg, nseg, thr, int(total.item()))
             if res[name]["reference_gpu"].get("ms"):
                 res[name]["speedup_vs_reference_gpu"] = res[name]["reference_gpu"]["ms"] * world / ms if world == 1 else None
+    return res
+
+
+def bench_decode(ops, dev, rank, iters=20):
+    """Grid-point decode (GridPostProcessor.get_boxes): R RoIs x 9 points x 28x28 logits, one stage; streaming read of
+    R*9*28*28*4 + 32R bytes.  R = 1000 (one test image) and 16000 (16 images)."""
+    from cpm_r_cnn_b200 import synthetic as sy
+    peak, _ = measured_peak()
+    res = {}
+    if rank != 0:
+        return res
+    gen = torch.Generator().manual_seed(77)
+    sub = ops.calc_sub_regions(9, 3, 56)
+    for R in (1000, 16000):
+        logits = (torch.randn(R, 9, 28, 28, generator=gen) * 2).to(dev)
+        boxes = sy.coco_like_boxes(gen, R).to(dev)
+        for _ in range(3):
+            ops.grid_decode(logits, boxes, sub, 0.5)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            ops.grid_decode(logits, boxes, sub, 0.5)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        nbytes = R * 9 * 28 * 28 * 4 + 32 * R
+        res["R%d" % R] = {"ms": ms, "rois_per_sec": R / (ms * 1e-3), "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                          "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
     return res
 
 

@@ -12,6 +12,7 @@ namespace cpm {
 int check_device_ptr(const void* p, const char* what);
 
 constexpr int kMaxPoints = 64;
+constexpr int kRegVec = 7;             // float4 per lane of the register-resident fast path: maps up to 896 logits (28x28 = 784)
 
 struct SubXY {
   int v[2 * kMaxPoints];
@@ -27,7 +28,7 @@ __device__ __forceinline__ void argmax_merge(float& bs, int& bi, float s, int i)
   }
 }
 
-__global__ void __launch_bounds__(288) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+__global__ void __launch_bounds__(288, 4) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                                            int P, int gs, int h, int w, SubXY sub, float ratio,
                                                            float* __restrict__ out_boxes, float* __restrict__ out_scores) {
   __shared__ float sc[kMaxPoints], ax[kMaxPoints], ay[kMaxPoints];
@@ -41,7 +42,37 @@ __global__ void __launch_bounds__(288) grid_decode_kernel(const float* __restric
     const float* m = logits + (r * P + p) * (long)hw;
     float bs = -1.f;
     int bi = 0x7fffffff;
-    if ((hw & 3) == 0) {
+    if ((hw & 3) == 0 && hw <= 4 * 32 * kRegVec) {
+      // Fast path: the map sits in registers (<= kRegVec float4 per lane, one streaming read).  sigmoid is monotone, so
+      // the arg-max of the sigmoids is found on the logits: pass 1 takes the largest logit M; pass 2 evaluates the sigmoid
+      // only where it could still equal (or, through rounding, exceed) sigmoid(M) -- logits within 1e-3 of M, and every
+      // logit >= 8, where fp32 sigmoids start to collide (1 - e^-x within an ulp of its neighbours) up to saturating at
+      // exactly 1.0 -- and applies the reference's rule there (largest sigmoid, first index among equals).  Below that
+      // band a logit's sigmoid is smaller than sigmoid(M) by more than 4 ulp, so the result equals the full evaluation.
+      const float4* m4 = reinterpret_cast<const float4*>(m);
+      const int n4 = hw >> 2;
+      float4 v[kRegVec];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < kRegVec; k++) {
+        const int i = lane + 32 * k;
+        v[k] = i < n4 ? __ldg(m4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float t = fminf(mx - 1e-3f, 8.0f);
+      // (NaN logits fail `>= t` and fmaxf ignores them, so they never win -- as in the reference's `>` comparison; an
+      //  all-NaN map leaves bi unset and decodes as index 0 below)
+#pragma unroll
+      for (int k = 0; k < kRegVec; k++) {
+        const int i = 4 * (lane + 32 * k);
+        if (v[k].x >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].x), i + 0);
+        if (v[k].y >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].y), i + 1);
+        if (v[k].z >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].z), i + 2);
+        if (v[k].w >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].w), i + 3);
+      }
+    } else if ((hw & 3) == 0) {
       const float4* m4 = reinterpret_cast<const float4*>(m);
       for (int i = lane; i < hw / 4; i += 32) {
         const float4 v = __ldg(m4 + i);

@@ -424,6 +424,53 @@ def test_grid_decode_random_vs_oracle():
     np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=1e-6, atol=1e-6)
 
 
+def test_grid_decode_saturation_ties_and_nan():
+    """The register fast path finds the arg-max on the logits and evaluates the sigmoid only near the maximum and in the
+    band where fp32 sigmoids collide (>= 8, saturating to exactly 1.0 from ~17): the reference's rule -- largest sigmoid,
+    FIRST index among equals (torch.max on the CPU, inference.py:204-207) -- must survive exact ties, saturated maps,
+    constant maps, huge negatives and NaNs.  Checked against the oracle (full evaluation, first index)."""
+    gen = torch.Generator().manual_seed(5)
+    R = 64
+    logits = torch.randn(R, 9, 28, 28, generator=gen) * 2
+    flat = logits.view(R, 9, -1)
+    for r in range(R):
+        for p in range(9):
+            kind = (r * 9 + p) % 8
+            idx = torch.randperm(784, generator=gen)[:6]
+            if kind == 0:
+                flat[r, p, idx] = torch.tensor([20.0, 25.0, 30.0, 17.5, 40.0, 19.0])     # all saturate to 1.0: first index wins
+            elif kind == 1:
+                flat[r, p, idx[:3]] = 5.0                                                 # exact tie at a moderate value
+            elif kind == 2:
+                flat[r, p] = 0.25                                                         # constant map -> index 0
+            elif kind == 3:
+                flat[r, p] = -80.0 - torch.rand(784, generator=gen)                       # sigmoid underflows towards 0
+            elif kind == 4:
+                flat[r, p, idx] = torch.tensor([12.0, 12.004, 12.008, 11.999, 12.002, 9.0])   # collision band: distinct logits,
+            elif kind == 5:                                                               # sigmoids an ulp or less apart
+                flat[r, p, idx] = torch.tensor([16.0, 16.3, 16.6, 16.9, 15.7, 16.45])
+            elif kind == 6:
+                flat[r, p, idx[0]] = float("nan")                                         # NaN never wins `>`
+    boxes = synthetic.coco_like_boxes(gen, R)
+    sub = ops.calc_sub_regions(9, 3, 56)
+    ref, rsc, rpos = oracle.grid_decode(logits.numpy(), boxes.numpy(), sub, 0.5, return_aux=True)
+    out, sc = ops.grid_decode(logits.cuda(), boxes.cuda(), sub, 0.5, return_scores=True)
+    np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=1e-6, atol=1e-6)
+    # positions: exact wherever the winning sigmoid is unique in fp32 or saturated/tied exactly (kinds 0-3, 6, 7); in the
+    # collision band (kinds 4, 5) device expf and libm expf may round neighbours differently, so only the score is pinned
+    kinds = (np.arange(R * 9) % 8).reshape(R, 9)
+    safe = ~np.isin(kinds, (4, 5)).any(axis=1)
+    assert safe.sum() == 0 or np.allclose(out.cpu().numpy()[safe], ref[safe], rtol=1e-5, atol=1e-3)
+    # every RoI mixes kinds, so also compare per point through the scores' argmax consistency: decode of a map whose
+    # winner is unambiguous must match regardless of its neighbours
+    only = torch.randn(8, 9, 28, 28, generator=gen)
+    only.view(8, 9, -1)[:, :, 100] = 30.0
+    only.view(8, 9, -1)[:, :, 50] = 31.0          # both saturate: index 50 (first) must win on every point
+    o2 = ops.grid_decode(only.cuda(), boxes[:8].cuda(), sub, 0.5)
+    r2 = oracle.grid_decode(only.numpy(), boxes[:8].numpy(), sub, 0.5)
+    np.testing.assert_allclose(o2.cpu().numpy(), r2, rtol=1e-5, atol=1e-3)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the reference's own CUDA kernels, live (oracle/_ref/pet_ref_cuda.so = unmodified ROIAlign_cuda.cu + ml_nms.cu built by
 # oracle/build_ref.py in the build container; it travels to the GPU box with the snapshot)

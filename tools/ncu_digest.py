@@ -62,12 +62,14 @@ for rep in sys.argv[1:]:
         scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(unit, 1.0)
         print("  [%d] %s  grid %s x block %s" % (n, name, g('launch__grid_size'), g('launch__block_size')))
         def mb(key, per=1.0):
-            if key not in h or r[h.index(key)] in ("", "?"):
+            if key not in h or not r[h.index(key)].replace(".", "").replace("e", "").replace("+", "").replace("-", "").isdigit():
                 return float("nan")
             u = rows[1][h.index(key)]
             return float(r[h.index(key)]) * per * {"Mbyte": 1, "Gbyte": 1e3, "Kbyte": 1e-3, "byte": 1e-6, "sector": 32e-6, "": 32e-6}.get(u, 1)
+        dur_us = float(g('gpu__time_duration.sum')) * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}.get(
+            rows[1][h.index('gpu__time_duration.sum')], 1.0)
         print("    duration %.1f us | DRAM read %.1f MB + write %.1f MB = traffic %.1f MB | L2 sectors %.0f MB | L1 sectors %.0f MB" % (
-            float(g('gpu__time_duration.sum')), rd * scale / 1e6, wr * scale / 1e6, (rd + wr) * scale / 1e6,
+            dur_us, rd * scale / 1e6, wr * scale / 1e6, (rd + wr) * scale / 1e6,
             mb('lts__t_sectors.sum'), mb('SM_B.TriageCompute.l1tex__t_sectors.sum')))
         print("    warp instr %.1f M | IPC/SM %.2f | warps active %.0f%% | regs %s | smem dyn %s + static %s KB | CTAs/SM limits: regs %s, smem %s, warps %s" % (
             float(g('smsp__inst_executed.sum')) / 1e6, float(g('sm__inst_executed.avg.per_cycle_elapsed')),
