@@ -185,6 +185,83 @@ __global__ void __launch_bounds__(256) roi_align_fwd_nhwc_any(PyramidView pv, co
   }
 }
 
+// bf16 storage, fp32 arithmetic (new on this path; the reference computes half inputs in fp32 through
+// apex.amp.float_function, roi_align.py:76, after a full-size cast of the feature maps).  Same structure as the kernel
+// above with a lane owning 8 channels: every tap is one 16-byte bf16x8 load, a warp covers 256 channels; the pooled block
+// is rounded to bf16 once, at the end (round-to-nearest-even), and leaves through a bf16 shared-memory tile.
+constexpr int kChunkB = 256;
+
+__global__ void __launch_bounds__(256) roi_align_fwd_nhwc_bf16(PyramidView pv, const float* __restrict__ rois, int PH, int PW,
+                                                                int sr, int aligned, MapperView mp,
+                                                                const int* __restrict__ roi_levels,
+                                                                __nv_bfloat16* __restrict__ out, int chunks, int S) {
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  __nv_bfloat16* tileb = reinterpret_cast<__nv_bfloat16*>(tile_raw);
+  const int C = pv.channels;
+  const long n = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * kChunkB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int cc = min(kChunkB, C - c0);         // channels in this chunk (multiple of 8)
+  const float* roi = rois + 5 * n;
+  const int l = roi_level(roi, pv, mp, roi_levels, n);
+  const int PP = PH * PW;
+  bool done = false;
+  if (l >= 0 && l < pv.num_levels) {
+    const int H = pv.H[l], W = pv.W[l];
+    RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, sr, aligned != 0);
+    if (g.b >= 0 && g.b < pv.batch) {
+      done = true;
+      const int cnt_i = g.gh * g.gw;
+      const float count = (float)(cnt_i > 1 ? cnt_i : 1);
+      const bool active = 8 * lane < cc;
+      const uint4* f = reinterpret_cast<const uint4*>((const __nv_bfloat16*)pv.ptr[l] + (long)g.b * H * W * C + c0) + lane;
+      const long C8 = C >> 3;
+      for (int bin = warp; bin < PP; bin += nwarps) {
+        const int ph = bin / PW, pw = bin % PW;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0.f;
+        for (int iy = 0; iy < g.gh; iy++) {
+          const float y = g.start_h + ph * g.bin_h + static_cast<float>(iy + .5f) * g.bin_h / static_cast<float>(g.gh);
+          const AxisTap ty = axis_tap(y, H);
+          for (int ix = 0; ix < g.gw; ix++) {
+            const float x = g.start_w + pw * g.bin_w + static_cast<float>(ix + .5f) * g.bin_w / static_cast<float>(g.gw);
+            const AxisTap tx = axis_tap(x, W);
+            if (!(ty.valid && tx.valid) || !active) continue;
+            const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+            const uint4 v1 = __ldg(f + ((long)ty.lo * W + tx.lo) * C8);
+            const uint4 v2 = __ldg(f + ((long)ty.lo * W + tx.hi) * C8);
+            const uint4 v3 = __ldg(f + ((long)ty.hi * W + tx.lo) * C8);
+            const uint4 v4 = __ldg(f + ((long)ty.hi * W + tx.hi) * C8);
+            const unsigned a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w};
+            const unsigned a3[4] = {v3.x, v3.y, v3.z, v3.w}, a4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {      // a 32-bit word holds two bf16: the low half is the even channel
+              acc[2 * k] += tap4(w1, __uint_as_float(a1[k] << 16), w2, __uint_as_float(a2[k] << 16),
+                                 w3, __uint_as_float(a3[k] << 16), w4, __uint_as_float(a4[k] << 16));
+              acc[2 * k + 1] += tap4(w1, __uint_as_float(a1[k] & 0xffff0000u), w2, __uint_as_float(a2[k] & 0xffff0000u),
+                                     w3, __uint_as_float(a3[k] & 0xffff0000u), w4, __uint_as_float(a4[k] & 0xffff0000u));
+            }
+          }
+        }
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) tileb[(8 * lane + k) * S + bin] = __float2bfloat16_rn(acc[k] / count);
+        }
+      }
+    }
+  }
+  if (!done)
+    for (int e = threadIdx.x; e < cc * PP; e += blockDim.x) tileb[(e / PP) * S + e % PP] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  __nv_bfloat16* o = out + ((long)n * C + c0) * PP;
+  const int total = cc * PP;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e / PP, b = e - c * PP;
+    o[e] = tileb[c * S + b];
+  }
+}
+
 // Compile-time-shaped kernel (the CPM head's 7x7 and 14x14 poolers with sampling_ratio 2, config.py:881-886):
 // a warp owns one row of PW bins and keeps all PW accumulators (4 channels each) in registers while it sweeps the
 // row's G*PW sample columns left to right, G sample rows one after the other -- the reference's summation order
@@ -700,8 +777,23 @@ extern "C" int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d
     return CPM_OK;
   }
   if (feat->dtype == CPM_BF16) {
-    set_error("bf16 pyramids need the NHWC kernel (layout NHWC, bilinear, C %% 8 == 0)");
-    return CPM_ERR_UNSUPPORTED;
+    bool ok = feat->layout == CPM_LAYOUT_NHWC && interpolation == CPM_INTERP_BILINEAR && feat->channels % 8 == 0 &&
+              pooled_layout == CPM_POOLED_KCHW && ((uintptr_t)d_out & 1) == 0;
+    for (int l = 0; ok && l < feat->num_levels; l++) ok = ((uintptr_t)feat->d_level[l] & 15) == 0;
+    const int S = PP | 1;
+    const int chunksb = (feat->channels + kChunkB - 1) / kChunkB;
+    const size_t smem_b = (size_t)kChunkB * S * sizeof(__nv_bfloat16);
+    if (!ok || smem_b > 200 * 1024 || (long)K * chunksb >= (1L << 31)) {
+      set_error("bf16 pyramids need layout NHWC, bilinear interpolation, C %% 8 == 0, 16-byte aligned maps, a (K,C,PH,PW) "
+                "bf16 output and PH*PW <= 399 (rois stay fp32)");
+      return CPM_ERR_UNSUPPORTED;
+    }
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(roi_align_fwd_nhwc_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    roi_align_fwd_nhwc_bf16<<<(unsigned)(K * chunksb), 256, smem_b, st>>>(pv, (const float*)d_rois, pooled_h, pooled_w,
+                                                                           sampling_ratio, aligned, mp, d_roi_levels,
+                                                                           (__nv_bfloat16*)d_out, chunksb, S);
+    CPM_CHECK_LAUNCH();
+    return CPM_OK;
   }
   const int threads = 256;
   long blocks = (total + threads - 1) / threads;

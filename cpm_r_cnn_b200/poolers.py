@@ -94,6 +94,7 @@ class Pooler(nn.Module):
         # Extension (not in the reference): set to torch.channels_last for heads whose convolutions run in channels_last
         # (the 14x14 grid head); the pooled tensor then has channels_last strides and its gradient is read in place.
         self.pooled_memory_format = torch.contiguous_format
+        self.native_bf16 = False      # extension: feed bf16 feature maps to the bf16x8 kernel instead of casting to fp32
 
     def convert_to_roi_format(self, boxes):
         """poolers.py:90-101: (K,5) [image index, x1, y1, x2, y2] in the boxes' dtype."""
@@ -110,9 +111,11 @@ class Pooler(nn.Module):
         rois = self.convert_to_roi_format(boxes)
         if num_levels == 1:
             self.poolers[0].pooled_memory_format = self.pooled_memory_format
+            self.poolers[0].native_bf16 = self.native_bf16
             return self.poolers[0](x[0], rois)
-        levels = [_float_function(t) for t in list(x)[:num_levels]]
-        rois = _float_function(rois).to(levels[0].dtype)
+        levels = [_float_function(t, self.native_bf16) for t in list(x)[:num_levels]]
+        rois = _float_function(rois)
+        rois = rois.to(torch.float32 if levels[0].dtype == torch.bfloat16 else levels[0].dtype)
         cfg = (self.output_size, self.scales[:len(levels)], self.sampling_ratio, self.aligned,
                INTERPOLATION_METHOD[self.interpolation], self.map_levels.c_struct(),
                self.pooled_memory_format == torch.channels_last)

@@ -61,6 +61,8 @@ def _prepare_levels(levels, interpolation):
     dt = levels[0].dtype
     if dt == torch.float32 and interpolation == 0 and levels[0].shape[1] % 4 == 0:
         return [stage_nhwc(t) for t in levels], _lib.NHWC
+    if dt == torch.bfloat16:
+        return [stage_nhwc(t) for t in levels], _lib.NHWC
     return [t.contiguous() for t in levels], _lib.NCHW
 
 
@@ -74,12 +76,17 @@ def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, i
         _lib.require_cuda(t, "input")
     _lib.require_cuda(rois, "rois")
     x0 = levels[0]
-    if rois.dtype != x0.dtype or rois.device != x0.device:
+    bf16 = x0.dtype == torch.bfloat16      # native bf16 storage (extension): rois stay fp32, arithmetic is fp32
+    if (rois.dtype != (torch.float32 if bf16 else x0.dtype)) or rois.device != x0.device:
         # at::checkAllSameGPU / checkAllSameType, ROIAlign_cuda.cu:381-382
         raise RuntimeError("cpm_ops: input and rois must have the same dtype and device (got %s/%s, %s/%s)"
                            % (x0.dtype, x0.device, rois.dtype, rois.device))
-    if x0.dtype not in (torch.float32, torch.float64):
-        raise RuntimeError("cpm_ops: roi_align supports float32 and float64 inputs (got %s)" % x0.dtype)
+    if x0.dtype not in (torch.float32, torch.float64, torch.bfloat16):
+        raise RuntimeError("cpm_ops: roi_align supports float32, float64 and (native, opt-in) bfloat16 inputs (got %s)"
+                           % x0.dtype)
+    if bf16 and (interpolation != 0 or x0.shape[1] % 8 != 0):
+        raise RuntimeError("cpm_ops: the bf16 path needs bilinear interpolation and C % 8 == 0")
+    channels_last = channels_last and not bf16
     ph, pw = output_size
     K, C = rois.shape[0], x0.shape[1]
     out = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device,
@@ -111,6 +118,11 @@ def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_rat
     """Dense gradients of every level: list[(B,C,H_l,W_l)] (channels_last strides on the NHWC path)."""
     _lib.require_cuda(grad_output, "grad_output")
     mode = BACKWARD_MODE if mode is None else mode
+    if grad_output.dtype == torch.bfloat16:
+        # bf16 pooled gradient (native bf16 forward): accumulate the dense gradient in fp32, round once at the end
+        grads = pooler_backward(grad_output.float(), shapes, scales, rois, output_size, sampling_ratio, aligned,
+                                interpolation, mapper, mode)
+        return [g.to(torch.bfloat16) for g in grads]
     ph, pw = output_size
     K = rois.shape[0]
     dt, dev = grad_output.dtype, grad_output.device
@@ -173,8 +185,11 @@ class _ROIAlign(Function):
 roi_align = _ROIAlign.apply
 
 
-def _float_function(x):
-    """apex.amp.float_function (roi_align.py:76): half inputs are computed in fp32."""
+def _float_function(x, keep_bf16=False):
+    """apex.amp.float_function (roi_align.py:76): half inputs are computed in fp32.  keep_bf16 (ROIAlign.native_bf16 /
+    Pooler.native_bf16, an extension) hands bf16 feature maps to the bf16x8 kernel instead of casting them."""
+    if keep_bf16 and x.dtype == torch.bfloat16:
+        return x
     return x.float() if x.dtype in (torch.float16, torch.bfloat16) else x
 
 
@@ -193,14 +208,17 @@ class ROIAlign(nn.Module):
         # strides -- for heads that run their convolutions in channels_last.  The default is the reference's layout
         # (heads that flatten with x.view(K, -1), cls_heads.py:43, need it).
         self.pooled_memory_format = torch.contiguous_format
+        # Extension: consume bf16 feature maps as stored (bf16x8 loads, fp32 arithmetic, bf16 output) instead of the
+        # reference's cast-to-fp32 (apex.amp.float_function)
+        self.native_bf16 = False
 
     def forward(self, input, rois):
         """input: NCHW images (any strides); rois: Bx5 boxes, first column = index into N, then xyxy."""
         assert rois.dim() == 2 and rois.size(1) == 5
         _ROIAlign.pooled_channels_last = self.pooled_memory_format == torch.channels_last
         try:
-            return roi_align(_float_function(input), _float_function(rois), self.output_size, self.spatial_scale,
-                             self.sampling_ratio, self.aligned, self.interpolation_method)
+            return roi_align(_float_function(input, self.native_bf16), _float_function(rois), self.output_size,
+                             self.spatial_scale, self.sampling_ratio, self.aligned, self.interpolation_method)
         finally:
             _ROIAlign.pooled_channels_last = False
 
