@@ -472,6 +472,20 @@ constexpr int SROW = kChunk + 4;       // floats per staged bin (528 B: rows sta
 constexpr int kRound = 2 * kTileThreads;   // RoIs of the (level, image) list scanned per round
 constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the tables hold (the path needs P * G <= 32)
 
+// per bin-column count nq (1..32): bin rows per item min(MAXP, NBUF / nq), and the multiplier with
+// pq / nq == (pq * magic) >> 16 for pq < 64 (the item generator runs on one thread: no integer divisions there)
+struct ItemTables {
+  unsigned char npg[33];
+  unsigned int magic[33];
+  constexpr ItemTables() : npg(), magic() {
+    for (int n = 1; n <= 32; n++) {
+      npg[n] = (unsigned char)(NBUF / n < MAXP ? NBUF / n : MAXP);
+      magic[n] = (65536u + n - 1) / n;
+    }
+  }
+};
+__constant__ ItemTables kItemTables = ItemTables();
+
 struct __align__(16) Item {
   long long gofs;                      // float offset of the sub-block's first element inside grad_out
   int r, p0, np, q0, nq, nb;
@@ -613,7 +627,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
           if (gp < pA) gp = pA;
           if (gp <= pB) {
             const int nq = qB - qA + 1;
-            const int np = min(min(MAXP, NBUF / nq), pB - gp + 1);
+            const int np = min((int)kItemTables.npg[nq], pB - gp + 1);
             const int r = sm.cand[gci];
             out.r = r;
             out.p0 = gp;
@@ -621,7 +635,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
             out.q0 = qA;
             out.nq = nq;
             out.nb = np * nq;
-            out.magic = (65536u + nq - 1) / nq;
+            out.magic = kItemTables.magic[nq];
             out.valid = 1;
             out.gofs = GO_CL ? ((long long)r * PP + gp * PW + qA) * C + c0
                              : ((long long)r * C + c0) * PP + gp * PW + qA;
