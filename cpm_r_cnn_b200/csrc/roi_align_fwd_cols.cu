@@ -18,6 +18,8 @@
 //           accumulators stay in registers, no dynamic register indexing, no per-sample control flow.
 //   out   = finished bins go to a shared-memory tile laid out exactly like the (K, C, PH, PW) output; the tile leaves
 //           with cp.async.bulk (one 25 KB bulk store per CTA at 7x7, one 784 B store per channel at 14x14).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cpm {
@@ -72,10 +74,8 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void bulk_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
@@ -247,7 +247,7 @@ __device__ __forceinline__ void run_nw(const char* base, const unsigned (&rowoff
 template <int NG, bool OCL>
 __global__ void __launch_bounds__(224 * NG, NG == 1 ? 3 : 2)
 roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int aligned, MapperView mp,
-                   const int* __restrict__ roi_levels, float* __restrict__ out, int chunks) {
+                   const int* __restrict__ roi_levels, float* __restrict__ out, int chunks, int cpc) {
   constexpr int P = kBins * NG;            // pooled height == width
   constexpr int PP = P * P;
   constexpr int LPR = 32 / NG;             // lanes per bin row
@@ -257,8 +257,11 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   __shared__ Tables<NG> tb;
 
   const int C = pv.channels;
-  const long n = blockIdx.x / chunks;
-  const int c0 = (blockIdx.x % chunks) * CH;
+  // One CTA pools `cpc` consecutive channel chunks of one RoI: the geometry, the column table and the bin-row taps are
+  // built once and reused (they do not depend on the channel), only the column loop and the output store repeat.
+  const int groups = chunks / cpc;
+  const long n = blockIdx.x / groups;
+  const int grp = blockIdx.x % groups;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* roi = rois + 5 * n;
   int l = 0;
@@ -267,12 +270,42 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   const bool ok = l >= 0 && l < pv.num_levels && geo.b >= 0 && geo.b < pv.batch;
   constexpr int kTileFloats = OCL ? 0 : CH * PP + SK * (CH / 4);      // a channels-last output needs no staging tile
   constexpr int kTileBytes = (kTileFloats * 4 + 15) & ~15;
-  if (!ok) {           // out-of-range level / image index: defined as zeros
-    if (OCL) {
-      for (int e = threadIdx.x; e < PP * (CH / 4); e += blockDim.x)
-        *reinterpret_cast<float4*>(out + ((size_t)n * PP + e / (CH / 4)) * C + c0 + 4 * (e % (CH / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool store_issuer = NG == 1 ? threadIdx.x == 0 : threadIdx.x < CH;      // threads that own bulk-store groups
+  // tile -> out[n, c0 : c0 + CH, :, :], asynchronous: the next chunk's column loop runs while the tile drains
+  auto store_tile = [&](int c0) {
+    if (OCL) return;
+    fence_async_smem();
+    __syncthreads();
+    float* o = out + ((size_t)n * C + c0) * PP;
+    if (NG == 1) {
+      if (threadIdx.x == 0) {
+        bulk_s2g(o, tile, CH * PP * 4);
+        bulk_commit();
+      }
     } else {
-      for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
+      if (threadIdx.x < CH) {
+        const int c = threadIdx.x;
+        bulk_s2g(o + (size_t)c * PP, tile + c * PP + SK * (c >> 2), PP * 4);
+        bulk_commit();
+      }
+    }
+  };
+  auto tile_free = [&](int ci) {        // before the tile is written again: its previous contents have left shared memory
+    if (OCL || ci == 0) return;
+    if (store_issuer) bulk_wait_read();
+    __syncthreads();
+  };
+  if (!ok) {           // out-of-range level / image index: defined as zeros
+    for (int ci = 0; ci < cpc; ci++) {
+      const int c0 = (grp * cpc + ci) * CH;
+      tile_free(ci);
+      if (OCL) {
+        for (int e = threadIdx.x; e < PP * (CH / 4); e += blockDim.x)
+          *reinterpret_cast<float4*>(out + ((size_t)n * PP + e / (CH / 4)) * C + c0 + 4 * (e % (CH / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
+      }
+      store_tile(c0);
     }
   } else {
     const int H = pv.H[l], W = pv.W[l];
@@ -380,7 +413,8 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
       const bool has_prev = lane > 0 && hi_prev >= 0;
       const bool newlo = lo >= 0 && (!has_prev || lo > hi_prev);
       const bool newhi = lo >= 0 && hi > lo && (!has_prev || hi > hi_prev);
-      const int chunk = blockIdx.x % chunks;
+      const int chunk = grp;
+      const int chunks = groups;       // the RoI's CTAs share the rows round-robin
       const char* img = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C);
       const unsigned bytes = (unsigned)(xmax - xmin + 1) * (unsigned)C * 4u;
       if (xany && newlo && lo % chunks == chunk) bulk_prefetch_l2(img + ((size_t)lo * W + xmin) * C * 4, bytes);
@@ -456,33 +490,22 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
       }
     }
     __syncthreads();
-    // ---- main loop ----
-    const char* base = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C + c0 + 4 * lr);
-    float* tptr = OCL ? out + ((size_t)n * PP + ph * P + kBins * g) * C + c0 + 4 * lr
-                      : tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
+    // ---- main loop, once per channel chunk ----
     ulonglong2* ring = reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(tile) + kTileBytes + warp * RingCfg<NG>::kWarpBytes) + lane;
-    if (nr == 2) run_nw_ring<NG, 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-    else if (nr == 3) run_nw_ring<NG, 3, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-    else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-    else run_nw<NG, 4, OCL>(base, rowoff, wy, tb, g, tptr, C);
-  }
-  if (OCL) return;
-  // ---- tile -> out[n, c0 : c0 + CH, :, :] ----
-  fence_async_smem();
-  __syncthreads();
-  float* o = out + ((size_t)n * C + c0) * PP;
-  if (NG == 1) {
-    if (threadIdx.x == 0) {
-      bulk_s2g(o, tile, CH * PP * 4);
-      bulk_commit_wait_read();
-    }
-  } else {
-    if (threadIdx.x < CH) {
-      const int c = threadIdx.x;
-      bulk_s2g(o + (size_t)c * PP, tile + c * PP + SK * (c >> 2), PP * 4);
-      bulk_commit_wait_read();
+    for (int ci = 0; ci < cpc; ci++) {
+      const int c0 = (grp * cpc + ci) * CH;
+      const char* base = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C + c0 + 4 * lr);
+      float* tptr = OCL ? out + ((size_t)n * PP + ph * P + kBins * g) * C + c0 + 4 * lr
+                        : tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
+      tile_free(ci);
+      if (nr == 2) run_nw_ring<NG, 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else if (nr == 3) run_nw_ring<NG, 3, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else run_nw<NG, 4, OCL>(base, rowoff, wy, tb, g, tptr, C);
+      store_tile(c0);
     }
   }
+  if (!OCL && store_issuer) bulk_wait_read();
 }
 
 }  // namespace fwdc
@@ -502,6 +525,13 @@ bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
   return true;
 }
 
+// channel chunks pooled by one CTA (must divide the chunk count)
+static int chunks_per_cta(int chunks, int want) {
+  if (const char* e = getenv("CPM_FWD_CPC")) want = atoi(e) > 0 ? atoi(e) : want;
+  while (want > 1 && chunks % want != 0) want--;
+  return want < 1 ? 1 : want;
+}
+
 int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
                     const int* lv, float* out, int out_channels_last, cudaStream_t st) {
   const size_t ring1 = 7 * fwdc::RingCfg<1>::kWarpBytes, ring2 = 14 * fwdc::RingCfg<2>::kWarpBytes;
@@ -512,13 +542,15 @@ int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
     auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<1, true> : fwdc::roi_align_fwd_cols<1, false>;
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    fn<<<(unsigned)(K * chunks), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
+    const int cpc = chunks_per_cta(chunks, 1);
+    fn<<<(unsigned)(K * (chunks / cpc)), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   } else {
     const int chunks = pv.channels / 64;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
     auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<2, true> : fwdc::roi_align_fwd_cols<2, false>;
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    fn<<<(unsigned)(K * chunks), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks);
+    const int cpc = chunks_per_cta(chunks, 2);
+    fn<<<(unsigned)(K * (chunks / cpc)), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   }
   CPM_CHECK_LAUNCH();
   return CPM_OK;
