@@ -600,3 +600,51 @@ def test_roi_align_native_bf16(pooled, sr):
     assert y.dtype == torch.bfloat16
     y.float().square().mean().backward()
     assert all(x.grad is not None and x.grad.dtype == torch.bfloat16 and torch.isfinite(x.grad.float()).all() for x in xg)
+
+
+def test_backward_many_rois_per_image_multi_round():
+    """More RoIs on one (level, image) than one scan round of the tile kernel holds (512): the per-tile candidate scan
+    runs in several rounds and the RoI order -- hence the bit pattern -- must not depend on the round boundaries."""
+    B, C, P = 1, 128, 7
+    H, W = 40, 56
+    gen = torch.Generator().manual_seed(4242)
+    K = 1400
+    s = torch.exp(torch.empty(K).uniform_(np.log(4.0), np.log(120.0), generator=gen))
+    cx, cy = torch.rand(K, generator=gen) * W * 4, torch.rand(K, generator=gen) * H * 4
+    rois = torch.stack([torch.zeros(K), cx - s / 2, cy - s / 2, cx + s / 2, cy + s / 2], 1)
+    go = torch.randn(K, C, P, P, generator=gen)
+    shapes = [(B, C, H, W)]
+    det = pooler_backward(go.cuda(), shapes, [0.25], rois.cuda(), (P, P), 2, False, 0, None, mode="deterministic")[0]
+    det2 = pooler_backward(go.cuda(), shapes, [0.25], rois.cuda(), (P, P), 2, False, 0, None, mode="deterministic")[0]
+    assert torch.equal(det, det2)
+    at = pooler_backward(go.cuda(), shapes, [0.25], rois.cuda(), (P, P), 2, False, 0, None, mode="atomic")[0]
+    gabs = pooler_backward(go.abs().cuda(), shapes, [0.25], rois.cuda(), (P, P), 2, False, 0, None, mode="atomic")[0]
+    close_sum(det.cpu(), at.cpu(), gabs.cpu(), 2e-5)
+    # a third of the RoIs against the scalar oracle (linearity: the gradient of a subset is the subset's gradient)
+    sub = slice(0, None, 3)
+    dsub = pooler_backward(go[sub].cuda(), shapes, [0.25], rois[sub].cuda(), (P, P), 2, False, 0, None)[0]
+    gref = oracle.roi_align_backward(go[sub].numpy(), rois[sub].numpy(), 0.25, P, P, B, C, H, W, 2, False)
+    gab2 = oracle.roi_align_backward(go[sub].abs().numpy(), rois[sub].numpy(), 0.25, P, P, B, C, H, W, 2, False)
+    close_sum(dsub.cpu(), gref, gab2)
+
+
+def test_inference_shaped_batch():
+    """configs[4]-shaped forward: 8 images x 1000 proposals through both poolers in one launch each, against the
+    reference-shaped generic kernel (full) and the oracle (sample)."""
+    B, C = 8, 256
+    gen = torch.Generator().manual_seed(99)
+    feats = synthetic.pyramid(gen, B, C, 200, 336)
+    rois = synthetic.coco_like_rois(gen, 1000, B, 200, 336)
+    xs = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    m = _lib.make_mapper(2, 5)
+    levels = oracle.level_map(rois.numpy(), 2, 5)
+    for P in (7, 14):
+        out = pooler_forward(xs, SCALES, rois.cuda(), (P, P), 2, False, 0, m)
+        gen_out = pooler_forward(xs, SCALES, rois.cuda(), (P, P), 2, False, 0, m, impl=_lib.FWD_GENERIC)
+        close(out.cpu(), gen_out.cpu())
+        idx = np.arange(0, rois.shape[0], 97)
+        for l in range(4):
+            sel = idx[levels[idx] == l]
+            if len(sel):
+                ref = oracle.roi_align_forward(feats[l].numpy(), rois.numpy()[sel], SCALES[l], P, P, 2, False)
+                close(out.cpu().numpy()[sel], ref)
