@@ -381,6 +381,7 @@ def run_ours(args):
     # ---- NMS half of the metric (configs[2]) ----
     nms = bench_nms(ops, dev, rank, world, dist, sync_all)
     decode = bench_decode(ops, dev, rank)
+    rpn = bench_rpn(ops, dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -417,7 +418,7 @@ def run_ours(args):
                                                           if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode}
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -491,6 +492,71 @@ def bench_decode(ops, dev, rank, iters=20):
         nbytes = R * 9 * 28 * 28 * 4 + 32 * R
         res["R%d" % R] = {"ms": ms, "rois_per_sec": R / (ms * 1e-3), "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
                           "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+    return res
+
+
+def bench_rpn(ops, dev, rank, iters=10):
+    """Next row: RPN proposal selection, 2 images x 5 FPN levels x 3 anchors of an 800x1344 image,
+    PRE_NMS_TOP_N_TRAIN 2000 / POST 2000 / FPN_POST_NMS_TOP_N_TRAIN 2000, thr 0.7 (training flavour, top-k over the
+    batch).  Ours = RPNPostProcessor (one decode launch + one batched NMS); reference_gpu = the reference's own loop
+    structure (inference.py:96-113: per level, per image clip -> remove_small_boxes -> torchvision nms) restated with the
+    same torch ops on the same GPU.  proposals/s = candidates entering the selection / time."""
+    import torchvision
+    res = {}
+    if rank != 0:
+        return res
+    gen = torch.Generator().manual_seed(5)
+    N, A, img = 2, 3, (1344, 800)
+    strides = (4, 8, 16, 32, 64)
+    shapes = [((800 + s - 1) // s, (1344 + s - 1) // s) for s in strides]
+    anchors, obj, reg = [], [], []
+    for (h, w), st in zip(shapes, strides):
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        ctr = torch.stack([xs, ys], -1).reshape(-1, 1, 2) * st + st / 2
+        half = torch.tensor([[5.6 * st, 2.8 * st], [4.0 * st, 4.0 * st], [2.8 * st, 5.6 * st]]).reshape(1, A, 2)
+        anchors.append(torch.cat([ctr - half, ctr + half - 1], -1).reshape(-1, 4).to(dev))
+        obj.append((torch.randn(N, A, h, w, generator=gen) * 2).to(dev))
+        reg.append((torch.randn(N, 4 * A, h, w, generator=gen) * 0.3).to(dev))
+    pre, post, thr, min_size, fpn_post = 2000, 2000, 0.7, 0, 2000
+    pp = ops.RPNPostProcessor(pre, post, thr, min_size, None, fpn_post, True).train()
+    alist = [[ops.BoxList(a, img) for a in anchors] for _ in range(N)]
+
+    def ours():
+        return pp(alist, obj, reg)
+
+    def reference_loop():
+        out = [[] for _ in range(N)]
+        for a, o, r in zip(anchors, obj, reg):
+            s, d, an = pp._level_candidates([ops.BoxList(a, img)] * N, o, r)
+            w_, h_ = (an[..., 2] - an[..., 0]) + 1, (an[..., 3] - an[..., 1]) + 1
+            cx, cy = an[..., 0] + 0.5 * w_, an[..., 1] + 0.5 * h_
+            dw, dh = d[..., 2].clamp(max=pp.box_coder.bbox_xform_clip), d[..., 3].clamp(max=pp.box_coder.bbox_xform_clip)
+            pcx, pcy, pw_, ph_ = d[..., 0] * w_ + cx, d[..., 1] * h_ + cy, torch.exp(dw) * w_, torch.exp(dh) * h_
+            boxes = torch.stack([pcx - 0.5 * pw_, pcy - 0.5 * ph_, pcx + 0.5 * pw_ - 1, pcy + 0.5 * ph_ - 1], -1)
+            for i in range(N):
+                b = boxes[i].clone()
+                b[:, 0::2].clamp_(min=0, max=img[0] - 1)
+                b[:, 1::2].clamp_(min=0, max=img[1] - 1)
+                keep = ((b[:, 2] - b[:, 0] + 1 >= min_size) & (b[:, 3] - b[:, 1] + 1 >= min_size)).nonzero().squeeze(1)
+                b, sc = b[keep], s[i][keep]
+                k = torchvision.ops.nms(b, sc, thr)[:post]
+                out[i].append((b[k], sc[k]))
+        allsc = torch.cat([sc for lv in out for _, sc in lv])
+        return torch.topk(allsc, min(fpn_post, allsc.numel()))[0]
+
+    cand = sum(min(pre, A * h * w) for (h, w) in shapes) * N
+    for name, fn in (("ours", ours), ("reference_gpu_loop", reference_loop)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / iters       # wall clock on purpose: both arms are host-sync bound
+        res[name] = {"ms": ms, "candidates": cand, "proposals_per_sec": cand / (ms * 1e-3)}
+    res["kept_per_image"] = [len(b) for b in ours()]
+    res["speedup"] = res["reference_gpu_loop"]["ms"] / res["ours"]["ms"]
     return res
 
 

@@ -14,8 +14,10 @@ from .grid_decode import GridPostProcessor, calc_sub_regions, grid_decode
 from .nms import batched_nms, ml_nms, nms
 from .poolers import LevelMapper, Pooler
 from .roi_align import ROIAlign, roi_align, stage_nhwc
+from .rpn import BoxCoder, RPNPostProcessor, rpn_decode
 from .structures import BoxList
 
 __all__ = ["ROIAlign", "roi_align", "stage_nhwc", "nms", "ml_nms", "batched_nms", "boxlist_nms", "boxlist_ml_nms",
            "boxlist_nms_legacy", "boxlist_ml_nms_legacy", "batched_boxlist_nms", "Pooler", "LevelMapper",
-           "grid_decode", "calc_sub_regions", "GridPostProcessor", "BoxList", "launch_count"]
+           "grid_decode", "calc_sub_regions", "GridPostProcessor", "BoxList", "launch_count", "RPNPostProcessor", "BoxCoder",
+           "rpn_decode"]

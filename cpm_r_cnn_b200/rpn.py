@@ -1,0 +1,159 @@
+"""RPN proposal selection as one batched device pipeline: same interface as the reference's
+RPNPostProcessor (pet/rcnn/modeling/rpn/inference.py:12-172).
+
+The reference loops in Python over FPN levels and, inside each level, over images: clip -> remove_small_boxes (nonzero,
+host sync) -> boxlist_nms, i.e. 5 x B tiny NMS calls per iteration.  Here the per-level top-k stays what it is in the
+reference (already batched over images: inference.py:84-93), and everything after it runs once for ALL (level, image)
+candidate sets: one cpm_rpn_decode launch (BoxCoder.decode + clip + size test), one cpm_nms_batched call (segments = level x
+image, post_nms_top_n per segment), then the cross-level selection.  The only host synchronisation is the read-back of the
+per-segment keep counts that sizes the returned BoxLists.
+"""
+import ctypes
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from .nms import batched_nms
+from .structures import BoxList
+
+
+class BoxCoder(object):
+    """The two attributes of pet/rcnn/utils/box_coder.py the decode needs (weights, bbox_xform_clip)."""
+
+    def __init__(self, weights=(1.0, 1.0, 1.0, 1.0), bbox_xform_clip=math.log(1000. / 16)):
+        self.weights = weights
+        self.bbox_xform_clip = bbox_xform_clip
+
+
+def permute_and_flatten(layer, N, A, C, H, W):
+    """pet/rcnn/utils/misc.py:6-10."""
+    layer = layer.view(N, -1, C, H, W)
+    layer = layer.permute(0, 3, 4, 1, 2)
+    return layer.reshape(N, -1, C)
+
+
+def rpn_decode(deltas, anchors, segments, segment_im_wh, weights, bbox_xform_clip, min_size):
+    """(M,4) deltas + anchors -> decoded, clipped boxes (M,4) and output segments (trash ids for too-small boxes)."""
+    _lib.require_cuda(deltas, "deltas")
+    M = deltas.shape[0]
+    S = segment_im_wh.shape[0]
+    num_trash = max(1, (M + 32767) // 32768)
+    deltas = deltas.float().contiguous()
+    anchors = anchors.float().contiguous()
+    segments = segments.to(torch.int32).contiguous()
+    segment_im_wh = segment_im_wh.float().contiguous()
+    boxes = torch.empty((M, 4), dtype=torch.float32, device=deltas.device)
+    seg_out = torch.empty((M,), dtype=torch.int32, device=deltas.device)
+    if M:
+        w = (ctypes.c_float * 4)(*[float(v) for v in weights])
+        with _lib.device_of(deltas):
+            _lib.check(_lib.lib().cpm_rpn_decode(_lib.ptr(deltas), _lib.ptr(anchors), _lib.ptr(segments),
+                                                 _lib.ptr(segment_im_wh), M, S, num_trash, w, float(bbox_xform_clip),
+                                                 float(min_size), _lib.ptr(boxes), _lib.ptr(seg_out),
+                                                 _lib.stream_ptr(deltas.device)))
+    return boxes, seg_out, S + num_trash
+
+
+class RPNPostProcessor(nn.Module):
+    """inference.py:12-42: RPNPostProcessor(pre_nms_top_n, post_nms_top_n, nms_thresh, min_size, box_coder=None,
+    fpn_post_nms_top_n=None, fpn_post_nms_per_batch=True); forward(anchors, objectness, box_regression, targets=None)."""
+
+    def __init__(self, pre_nms_top_n, post_nms_top_n, nms_thresh, min_size, box_coder=None, fpn_post_nms_top_n=None,
+                 fpn_post_nms_per_batch=True):
+        super(RPNPostProcessor, self).__init__()
+        self.pre_nms_top_n = pre_nms_top_n
+        self.post_nms_top_n = post_nms_top_n
+        self.nms_thresh = nms_thresh
+        self.min_size = min_size
+        if box_coder is None:
+            box_coder = BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
+        self.box_coder = box_coder
+        if fpn_post_nms_top_n is None:
+            fpn_post_nms_top_n = post_nms_top_n
+        self.fpn_post_nms_top_n = fpn_post_nms_top_n
+        self.fpn_post_nms_per_batch = fpn_post_nms_per_batch
+
+    def add_gt_proposals(self, proposals, targets):
+        """inference.py:44-66: ground-truth boxes join the proposals with objectness 1."""
+        out = []
+        for proposal, target in zip(proposals, targets):
+            gt = target.bbox.to(proposal.bbox.device, proposal.bbox.dtype)
+            merged = BoxList(torch.cat([proposal.bbox, gt], 0), proposal.size, proposal.mode)
+            merged.add_field("objectness", torch.cat([proposal.get_field("objectness"),
+                                                      torch.ones(gt.shape[0], device=gt.device)], 0))
+            out.append(merged)
+        return out
+
+    def _level_candidates(self, anchors, objectness, box_regression):
+        """inference.py:75-94, unchanged: sigmoid, per-image top-k, gather of deltas and anchors (all torch, batched)."""
+        N, A, H, W = objectness.shape
+        objectness = permute_and_flatten(objectness, N, A, 1, H, W).view(N, -1).sigmoid()
+        box_regression = permute_and_flatten(box_regression, N, A, 4, H, W)
+        pre_nms_top_n = min(self.pre_nms_top_n, A * H * W)
+        objectness, topk_idx = objectness.topk(pre_nms_top_n, dim=1, sorted=True)
+        batch_idx = torch.arange(N, device=objectness.device)[:, None]
+        box_regression = box_regression[batch_idx, topk_idx]
+        concat_anchors = torch.cat([a.bbox for a in anchors], dim=0).reshape(N, -1, 4)[batch_idx, topk_idx]
+        return objectness, box_regression, concat_anchors
+
+    def forward(self, anchors, objectness, box_regression, targets=None):
+        """anchors: list (images) of list (levels) of BoxList; objectness / box_regression: list (levels) of tensors
+        (N, A, H, W) / (N, 4A, H, W).  Returns list[BoxList] with field "objectness" (inference.py:115-143)."""
+        num_levels = len(objectness)
+        N = objectness[0].shape[0]
+        dev = objectness[0].device
+        _lib.require_cuda(objectness[0], "objectness")
+        image_sizes = [per_image[0].size for per_image in anchors]
+        scores, deltas, boxes_a, segs = [], [], [], []
+        for l, (a, o, b) in enumerate(zip(list(zip(*anchors)), objectness, box_regression)):
+            s, d, an = self._level_candidates(a, o, b)
+            k = s.shape[1]
+            scores.append(s.reshape(-1))
+            deltas.append(d.reshape(-1, 4))
+            boxes_a.append(an.reshape(-1, 4))
+            segs.append((l * N + torch.arange(N, device=dev, dtype=torch.int32))[:, None].expand(N, k).reshape(-1))
+        scores, deltas, boxes_a, segs = torch.cat(scores), torch.cat(deltas), torch.cat(boxes_a), torch.cat(segs)
+        S = num_levels * N
+        im_wh = torch.tensor([[float(w), float(h)] for (w, h) in image_sizes] * num_levels, dtype=torch.float32, device=dev)
+        boxes, seg_out, nseg_total = rpn_decode(deltas, boxes_a, segs, im_wh, self.box_coder.weights,
+                                                self.box_coder.bbox_xform_clip, self.min_size)
+        topk = self.post_nms_top_n if self.post_nms_top_n > 0 else 0      # boxlist_nms(max_proposals=...), :106-111
+        keep, counts, _ = batched_nms(boxes, scores, seg_out, nseg_total, self.nms_thresh, topk, sync=False)
+        counts_h = counts[:S].cpu().tolist()                              # the one host sync: sizes of the results
+        offs = [0]
+        for c in counts_h:
+            offs.append(offs[-1] + c)
+        boxlists = []
+        for i in range(N):
+            idx = torch.cat([keep[offs[l * N + i]:offs[l * N + i + 1]] for l in range(num_levels)])     # cat_boxlist order
+            bl = BoxList(boxes[idx], image_sizes[i], mode="xyxy")
+            bl.add_field("objectness", scores[idx])
+            boxlists.append(bl)
+        if num_levels > 1:
+            boxlists = self.select_over_all_levels(boxlists)
+        if self.training and targets is not None:
+            boxlists = self.add_gt_proposals(boxlists, targets)
+        return boxlists
+
+    def select_over_all_levels(self, boxlists):
+        """inference.py:145-172: training = top-k over the whole batch (Detectron convention), testing = per image."""
+        num_images = len(boxlists)
+        if self.training and self.fpn_post_nms_per_batch:
+            objectness = torch.cat([b.get_field("objectness") for b in boxlists], dim=0)
+            box_sizes = [len(b) for b in boxlists]
+            post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
+            _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
+            inds_mask = torch.zeros_like(objectness, dtype=torch.bool)
+            inds_mask[inds_sorted] = 1
+            inds_mask = inds_mask.split(box_sizes)
+            for i in range(num_images):
+                boxlists[i] = boxlists[i][inds_mask[i]]
+        else:
+            for i in range(num_images):
+                objectness = boxlists[i].get_field("objectness")
+                post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
+                _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
+                boxlists[i] = boxlists[i][inds_sorted]
+        return boxlists

@@ -194,6 +194,20 @@ CPM_API int cpm_grid_decode(const float* d_logits, const float* d_boxes, int64_t
                     const int32_t* sub_xy, float mapping_ratio, float* d_out_boxes, float* d_out_scores,
                     void* stream);
 
+/* ---- RPN proposal decode (next row) ---------------------------------------------
+ * For all (FPN level, image) candidate sets of a batch in one launch: BoxCoder.decode (box_coder.py:51-94),
+ * clip_to_image (bounding_box.py:294-304) and remove_small_boxes (boxlist_ops.py:104-118), the per-image body of
+ * RPNPostProcessor.forward_for_single_feature_map (rpn/inference.py:96-113) up to the NMS.
+ *   d_deltas, d_anchors (M,4) fp32; d_segments int32[M] in [0, num_segments); d_segment_im_wh (num_segments,2) = (width,
+ *   height) of each segment's image; weights = HOST float[4] (wx, wy, ww, wh); bbox_xform_clip = log(1000/16).
+ *   d_boxes (M,4) decoded + clipped; d_segments_out int32[M]: the input segment, or one of the num_trash trash segments
+ *   num_segments .. num_segments + num_trash - 1 for a box smaller than min_size (spread round-robin so that no trash
+ *   segment outgrows the NMS's per-segment limit) -- feed both to cpm_nms_batched with num_segments + num_trash segments. */
+CPM_API int cpm_rpn_decode(const float* d_deltas, const float* d_anchors, const int32_t* d_segments,
+                   const float* d_segment_im_wh, int64_t M, int64_t num_segments, int64_t num_trash,
+                   const float* weights, float bbox_xform_clip, float min_size, float* d_boxes, int32_t* d_segments_out,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,10 +216,55 @@ def gen_decode():
     np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
 
 
+def rpn_inputs(seed, N=2, A=3, level_shapes=((25, 42), (13, 21), (7, 11)), strides=(8, 16, 32), img=(336, 200)):
+    """Seeded RPN head outputs + grid anchors ((H, W, A) order, what the reference's AnchorGenerator emits) for a
+    200x336 image; regression scaled so that decoded boxes overlap heavily (NMS has work to do)."""
+    g = torch.Generator().manual_seed(seed)
+    anchors, obj, reg = [], [], []
+    for (h, w), st in zip(level_shapes, strides):
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        ctr = torch.stack([xs, ys], -1).reshape(-1, 1, 2) * st + st / 2
+        half = torch.tensor([[2.0 * st, 1.0 * st], [1.4 * st, 1.4 * st], [1.0 * st, 2.0 * st]][:A]).reshape(1, A, 2)
+        a = torch.cat([ctr - half, ctr + half - 1], -1).reshape(-1, 4)
+        anchors.append(a)
+        obj.append(torch.randn(N, A, h, w, generator=g) * 2)
+        reg.append(torch.randn(N, 4 * A, h, w, generator=g) * 0.4)
+    return anchors, obj, reg, img
+
+
+def gen_rpn():
+    """RPNPostProcessor (pet/rcnn/modeling/rpn/inference.py) end to end on CPU: training (top-k over the batch) and
+    testing (per image) behaviour, min_size 0 and 16."""
+    from pet.rcnn.modeling.rpn.inference import RPNPostProcessor
+    from pet.rcnn.utils.box_coder import BoxCoder
+    from pet.utils.data.structures.bounding_box import BoxList
+    anchors, obj, reg, img = rpn_inputs(2024)
+    N = obj[0].shape[0]
+    out = {"img_wh": np.array(img, np.int64), "N": np.array(N)}
+    for l in range(len(obj)):
+        out["anchors%d" % l], out["obj%d" % l], out["reg%d" % l] = anchors[l].numpy(), obj[l].numpy(), reg[l].numpy()
+    cases = {"train": (300, 60, 0.7, 0, 100, True), "test": (200, 50, 0.7, 0, 80, False), "minsize": (300, 60, 0.6, 16, 100, False)}
+    for tag, (pre, post, thr, min_size, fpn_post, training) in cases.items():
+        pp = RPNPostProcessor(pre, post, thr, min_size, BoxCoder(weights=(1.0, 1.0, 1.0, 1.0)), fpn_post, True)
+        pp.train(training)
+        alist = [[BoxList(a.clone(), img, mode="xyxy") for a in anchors] for _ in range(N)]
+        res = pp(alist, [o.clone() for o in obj], [r.clone() for r in reg])
+        out[tag + "_params"] = np.array([pre, post, thr, min_size, fpn_post, int(training)], np.float64)
+        for i, bl in enumerate(res):
+            out["%s_boxes%d" % (tag, i)] = bl.bbox.numpy()
+            out["%s_scores%d" % (tag, i)] = bl.get_field("objectness").numpy()
+    np.savez_compressed(os.path.join(HERE, "rpn.npz"), **out)
+
+
 def main():
     build_ref.build(cuda=False)
     ref = build_ref.load("pet_ref_cpu")
     install_shims(ref)
+    if "rpn" in sys.argv[1:]:
+        gen_rpn()
+        print("rpn.npz", os.path.getsize(os.path.join(HERE, "rpn.npz")))
+        return
+    gen_rpn()
     feats, rois = gen_roi_align(ref)
     gen_pooler(feats, rois)
     gen_levels()

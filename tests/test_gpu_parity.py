@@ -648,3 +648,86 @@ def test_inference_shaped_batch():
             if len(sel):
                 ref = oracle.roi_align_forward(feats[l].numpy(), rois.numpy()[sel], SCALES[l], P, P, 2, False)
                 close(out.cpu().numpy()[sel], ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# next row: RPN proposal selection as one batched device pipeline
+# ----------------------------------------------------------------------------------------------------------------
+def test_rpn_decode_vs_oracle():
+    from oracle import rpn as orpn
+    gen = torch.Generator().manual_seed(8)
+    M, S = 5000, 6
+    anchors = synthetic.coco_like_boxes(gen, M, 200, 336, 8.0, 150.0)
+    deltas = torch.randn(M, 4, generator=gen) * torch.tensor([0.5, 0.5, 1.5, 1.5])
+    deltas[::50, 2:] = 9.0                                   # beyond bbox_xform_clip = log(1000/16)
+    segs = torch.randint(0, S, (M,), generator=gen).to(torch.int32)
+    wh = torch.tensor([[336.0, 200.0], [300.0, 180.0]] * 3)
+    for min_size, weights in ((0.0, (1.0, 1.0, 1.0, 1.0)), (12.0, (10.0, 10.0, 5.0, 5.0))):
+        boxes, seg_out, nseg = ops.rpn_decode(deltas.cuda(), anchors.cuda(), segs.cuda(), wh.cuda(), weights,
+                                              np.log(1000. / 16), min_size)
+        ref = orpn.decode(deltas.numpy(), anchors.numpy(), weights)
+        ok_all = np.zeros(M, bool)
+        refc = np.empty_like(ref)
+        for s in range(S):
+            m = segs.numpy() == s
+            refc[m], ok_all[m] = orpn.clip_and_size(ref[m], wh[s, 0].item(), wh[s, 1].item(), min_size)
+        np.testing.assert_allclose(boxes.cpu().numpy(), refc, rtol=1e-5, atol=1e-3)     # device expf vs libm exp: ulps
+        so = seg_out.cpu().numpy()
+        ws, hs = refc[:, 2] - refc[:, 0] + 1, refc[:, 3] - refc[:, 1] + 1
+        clear = (np.abs(ws - min_size) > 1e-2) & (np.abs(hs - min_size) > 1e-2)
+        assert np.array_equal((so < S)[clear], ok_all[clear])
+        assert np.array_equal(so[so < S], segs.numpy()[so < S]) and so.max() < nseg
+
+
+@pytest.mark.parametrize("tag", ["train", "test", "minsize"])
+def test_rpn_postprocessor_golden(golden, tag):
+    """Same inputs as the reference's RPNPostProcessor run (CPU, tests/golden/rpn.npz): same number of proposals per
+    image, same scores (sigmoid: 1 ulp), boxes within 1e-3 px."""
+    g = golden("rpn")
+    pre, post, thr, min_size, fpn_post, training = g[tag + "_params"]
+    N, L = int(g["N"]), 3
+    img = tuple(int(v) for v in g["img_wh"])
+    pp = ops.RPNPostProcessor(int(pre), int(post), float(thr), float(min_size), ops.BoxCoder((1.0, 1.0, 1.0, 1.0)),
+                              int(fpn_post), True)
+    pp.train(bool(training))
+    anchors = [[ops.BoxList(cuda(g["anchors%d" % l]), img) for l in range(L)] for _ in range(N)]
+    res = pp(anchors, [cuda(g["obj%d" % l]) for l in range(L)], [cuda(g["reg%d" % l]) for l in range(L)])
+    for i, bl in enumerate(res):
+        rb, rs = g["%s_boxes%d" % (tag, i)], g["%s_scores%d" % (tag, i)]
+        assert len(bl) == rb.shape[0]
+        np.testing.assert_allclose(bl.get_field("objectness").cpu().numpy(), rs, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(bl.bbox.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_rpn_postprocessor_vs_oracle(training):
+    """COCO-shaped sizes: 4 images x 5 levels, pre_nms_top_n 1000: the batched pipeline (one decode launch, one NMS
+    launch over 20 segments) against the per-(level, image) numpy oracle fed with the same device sigmoid values."""
+    from oracle import rpn as orpn
+    gen = torch.Generator().manual_seed(77 + int(training))
+    N, A = 4, 3
+    shapes, strides, img = ((50, 84), (25, 42), (13, 21), (7, 11), (4, 6)), (4, 8, 16, 32, 64), (336, 200)
+    anchors, obj, reg = [], [], []
+    for (h, w), st in zip(shapes, strides):
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        ctr = torch.stack([xs, ys], -1).reshape(-1, 1, 2) * st + st / 2
+        half = torch.tensor([[4.0 * st, 2.0 * st], [2.8 * st, 2.8 * st], [2.0 * st, 4.0 * st]]).reshape(1, A, 2)
+        anchors.append(torch.cat([ctr - half, ctr + half - 1], -1).reshape(-1, 4))
+        obj.append(torch.randn(N, A, h, w, generator=gen) * 2)
+        reg.append(torch.randn(N, 4 * A, h, w, generator=gen) * 0.3)
+    kw = dict(pre_nms_top_n=1000, post_nms_top_n=300, nms_thresh=0.7, min_size=4.0, fpn_post_nms_top_n=500)
+    pp = ops.RPNPostProcessor(kw["pre_nms_top_n"], kw["post_nms_top_n"], kw["nms_thresh"], kw["min_size"], None,
+                              kw["fpn_post_nms_top_n"], True)
+    pp.train(training)
+    alist = [[ops.BoxList(a.cuda(), img) for a in anchors] for _ in range(N)]
+    l0 = ops.launch_count()
+    res = pp(alist, [o.cuda() for o in obj], [r.cuda() for r in reg])
+    assert ops.launch_count() - l0 <= 16                     # decode + keys, radix-sort passes, gather, sweep -- not 20 NMS calls
+    probs = [o.cuda().sigmoid().cpu().numpy() for o in obj]
+    ref = orpn.select([np.broadcast_to(a.numpy(), (N,) + tuple(a.shape)) for a in anchors], probs, [r.numpy() for r in reg],
+                      [img] * N, training=training, scores_are_probs=True,
+                      nms_fn=lambda b, s, t: oracle.nms(b, s, t, flavor=oracle.FLAVOR_TV_CUDA), **kw)
+    for bl, (rb, rs) in zip(res, ref):
+        assert len(bl) == rb.shape[0]
+        assert np.array_equal(bl.get_field("objectness").cpu().numpy(), rs)
+        np.testing.assert_allclose(bl.bbox.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)

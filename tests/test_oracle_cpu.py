@@ -121,3 +121,32 @@ def test_decode_matches_reference(golden):
     for stage, ratio in enumerate((1.0, 0.5, 0.25)):
         out = oracle.grid_decode(g["logits"], g["boxes"], sub, ratio)
         np.testing.assert_allclose(out, g["stage%d" % stage], rtol=1e-5, atol=1e-3)
+
+
+def _rpn_case(g, tag):
+    pre, post, thr, min_size, fpn_post, training = g[tag + "_params"]
+    N = int(g["N"])
+    L = 3
+    anchors = [np.broadcast_to(g["anchors%d" % l], (N,) + g["anchors%d" % l].shape) for l in range(L)]
+    obj = [g["obj%d" % l] for l in range(L)]
+    reg = [g["reg%d" % l] for l in range(L)]
+    sizes = [tuple(int(v) for v in g["img_wh"])] * N
+    return anchors, obj, reg, sizes, dict(pre_nms_top_n=int(pre), post_nms_top_n=int(post), nms_thresh=float(thr),
+                                          min_size=float(min_size), fpn_post_nms_top_n=int(fpn_post), training=bool(training))
+
+
+@pytest.mark.parametrize("tag", ["train", "test", "minsize"])
+def test_rpn_selection_oracle_matches_reference(golden, tag):
+    """oracle/rpn.py (numpy restatement) against the reference's RPNPostProcessor run on CPU (tests/golden/rpn.npz).
+    The sigmoid is taken from torch here (the reference's own op) so that the comparison pins decode, clip, size test,
+    NMS and the cross-level selection bit for bit; np.exp vs torch.exp in the decode is within an ulp."""
+    from oracle import rpn
+    g = golden("rpn")
+    anchors, obj, reg, sizes, kw = _rpn_case(g, tag)
+    probs = [torch.from_numpy(o).sigmoid().numpy() for o in obj]
+    res = rpn.select(anchors, probs, reg, sizes, scores_are_probs=True, **kw)
+    for i, (b, s) in enumerate(res):
+        rb, rs = g["%s_boxes%d" % (tag, i)], g["%s_scores%d" % (tag, i)]
+        assert b.shape == rb.shape
+        assert np.array_equal(s, rs)
+        np.testing.assert_allclose(b, rb, rtol=2e-6, atol=2e-4)
