@@ -382,6 +382,7 @@ def run_ours(args):
     nms = bench_nms(ops, dev, rank, world, dist, sync_all)
     decode = bench_decode(ops, dev, rank)
     rpn = bench_rpn(ops, dev, rank)
+    det = bench_detect(ops, dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -418,7 +419,7 @@ def run_ours(args):
                                                           if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn}
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -556,6 +557,68 @@ def bench_rpn(ops, dev, rank, iters=10):
         ms = (time.perf_counter() - t0) * 1e3 / iters       # wall clock on purpose: both arms are host-sync bound
         res[name] = {"ms": ms, "candidates": cand, "proposals_per_sec": cand / (ms * 1e-3)}
     res["kept_per_image"] = [len(b) for b in ours()]
+    res["speedup"] = res["reference_gpu_loop"]["ms"] / res["ours"]["ms"]
+    return res
+
+
+def bench_detect(ops, dev, rank, iters=5):
+    """Next row: detection post-processing, 16 images x 1000 proposals x 81 classes, score > 0.03,
+    thr 0.3.  Ours = CLSPostProcessor (whole batch, one NMS launch); reference_gpu = the reference's per-image loop
+    (inference.py:91-124: repeat, clip, numpy label build + H2D, mask, `_C.ml_nms` = the unmodified ml_nms.cu when
+    oracle/_ref is present, else torchvision.ops.batched_nms) with the same torch ops on the same GPU."""
+    import numpy as np
+    import torchvision
+    from cpm_r_cnn_b200 import synthetic as sy
+    res = {}
+    if rank != 0:
+        return res
+    gen = torch.Generator().manual_seed(21)
+    B, R, C, img = 16, 1000, 81, (sy.IMG_W, sy.IMG_H)
+    boxes = [sy.coco_like_boxes(gen, R).to(dev) for _ in range(B)]
+    logits = torch.randn(B * R, C, generator=gen).to(dev)
+    pp = ops.CLSPostProcessor(0.03, 0.3)
+    blists = [ops.BoxList(b, img) for b in boxes]
+    try:
+        from oracle import build_ref
+        refk = build_ref.load("pet_ref_cuda")
+        ml = lambda b, s, l: refk.ml_nms(b, s, l, 0.3, 0)
+        op = "_C.ml_nms (reference ml_nms.cu, unmodified) per image"
+    except Exception:
+        ml = lambda b, s, l: torchvision.ops.batched_nms(b, s, l, 0.3)
+        op = "torchvision.ops.batched_nms per image (reference build unavailable)"
+
+    def ours():
+        return pp(logits, blists)
+
+    def reference_loop():
+        prob = torch.softmax(logits, -1)
+        out = []
+        for i in range(B):
+            p = prob[i * R:(i + 1) * R]
+            b = boxes[i].repeat(1, C).reshape(-1, 4)
+            b[:, 0::2].clamp_(min=0, max=img[0] - 1)
+            b[:, 1::2].clamp_(min=0, max=img[1] - 1)
+            sc = p.reshape(-1)
+            labels = torch.from_numpy(np.tile(np.arange(C), R)).to(dtype=torch.int64, device=dev)
+            fg = torch.from_numpy((np.arange(R * C) % C != 0).astype(int)).to(dtype=torch.bool, device=dev)
+            m = (sc > 0.03) & fg
+            keep = ml(b[m], sc[m], labels[m])
+            out.append(keep.numel())
+        return out
+
+    for name, fn in (("ours", ours), ("reference_gpu_loop", reference_loop)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            r = fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / iters
+        res[name] = {"ms": ms, "proposals_x_classes": B * R * (C - 1), "pairs_per_sec": B * R * (C - 1) / (ms * 1e-3)}
+    res["reference_gpu_loop"]["op"] = op
+    res["detections"] = sum(len(b) for b in ours())
+    res["same_count_as_reference"] = res["detections"] == sum(reference_loop())
     res["speedup"] = res["reference_gpu_loop"]["ms"] / res["ours"]["ms"]
     return res
 

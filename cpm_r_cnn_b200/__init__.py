@@ -10,6 +10,7 @@ from . import _lib
 from ._lib import launch_count
 from .boxlist_ops import (batched_boxlist_nms, boxlist_ml_nms, boxlist_ml_nms_legacy, boxlist_nms,
                           boxlist_nms_legacy)
+from .detect_postprocess import CLSPostProcessor
 from .grid_decode import GridPostProcessor, calc_sub_regions, grid_decode
 from .nms import batched_nms, ml_nms, nms
 from .poolers import LevelMapper, Pooler
@@ -20,4 +21,4 @@ from .structures import BoxList
 __all__ = ["ROIAlign", "roi_align", "stage_nhwc", "nms", "ml_nms", "batched_nms", "boxlist_nms", "boxlist_ml_nms",
            "boxlist_nms_legacy", "boxlist_ml_nms_legacy", "batched_boxlist_nms", "Pooler", "LevelMapper",
            "grid_decode", "calc_sub_regions", "GridPostProcessor", "BoxList", "launch_count", "RPNPostProcessor", "BoxCoder",
-           "rpn_decode"]
+           "rpn_decode", "CLSPostProcessor"]

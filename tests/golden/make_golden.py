@@ -256,15 +256,66 @@ def gen_rpn():
     np.savez_compressed(os.path.join(HERE, "rpn.npz"), **out)
 
 
+def gen_detect():
+    """CLSPostProcessor.forward (grid_cascade_rcnn/inference.py:59-124) on CPU.  `_C.ml_nms` has no CPU build
+    (ml_nms.h:38), so for this fixture only it is bound to the oracle's label-gated NMS (itself pinned to the reference's
+    kernel by nms.npz); what the fixture pins is the reference's Python around it: softmax, per-class repeat, clip, score
+    gate, numpy label build, BoxList indexing."""
+    import oracle
+    import pet.lib.ops.boxlist_ops as blo
+    from pet.rcnn.modeling.grid_cascade_rcnn.inference import CLSPostProcessor
+    from pet.utils.data.structures.bounding_box import BoxList
+
+    def ml_nms_cpu(boxes, scores, labels, thr, topk):
+        keep = oracle.nms(boxes.numpy(), scores.numpy(), float(thr), labels=labels.numpy(), topk=int(topk),
+                          flavor=oracle.FLAVOR_ML_CUDA)
+        return torch.from_numpy(keep)
+    blo._box_ml_nms = ml_nms_cpu
+    g = torch.Generator().manual_seed(99)
+    C, img = 21, (336, 200)
+    counts = [37, 0, 52]
+    boxes = []
+    for n in counts:
+        b = coco_like_rois(g, max(n - 8, 0), img[1], img[0], 1)[:n, 1:] if n else torch.zeros(0, 4)
+        boxes.append(b)
+    logits = torch.randn(sum(counts), C, generator=g) * 2.5
+    out = {"logits": logits.numpy(), "counts": np.array(counts), "img_wh": np.array(img), "params": np.array([0.03, 0.3])}
+    for i, b in enumerate(boxes):
+        out["boxes%d" % i] = b.numpy()
+    pp = CLSPostProcessor(0.03, 0.3)
+    res = pp(logits.clone(), [BoxList(b.clone(), img, mode="xyxy") for b in boxes])
+    for i, bl in enumerate(res):
+        out["res_boxes%d" % i] = bl.bbox.numpy()
+        out["res_scores%d" % i] = bl.get_field("scores").numpy()
+        out["res_labels%d" % i] = bl.get_field("labels").numpy()
+    # rescoring branch (:62-76)
+    bls = []
+    for b in boxes:
+        bl = BoxList(b.clone(), img, mode="xyxy")
+        bl.add_field("scores", torch.rand(len(b), generator=g))
+        bl.add_field("labels", torch.randint(1, C, (len(b),), generator=g))
+        bls.append(bl)
+    rl = torch.randn(counts[0], C, generator=g)
+    out["rescore_logits"] = rl.numpy()
+    out["rescore_in_scores"] = bls[0].get_field("scores").numpy()
+    out["rescore_in_labels"] = bls[0].get_field("labels").numpy()
+    r = CLSPostProcessor(0.03, 0.3)(rl, [bls[0]], rescore=True)
+    out["rescore_out"] = r[0].get_field("scores").numpy()
+    np.savez_compressed(os.path.join(HERE, "detect.npz"), **out)
+
+
 def main():
     build_ref.build(cuda=False)
     ref = build_ref.load("pet_ref_cpu")
     install_shims(ref)
-    if "rpn" in sys.argv[1:]:
-        gen_rpn()
-        print("rpn.npz", os.path.getsize(os.path.join(HERE, "rpn.npz")))
+    only = [a for a in sys.argv[1:] if a in ("rpn", "detect")]
+    if only:
+        for a in only:
+            {"rpn": gen_rpn, "detect": gen_detect}[a]()
+            print(a + ".npz", os.path.getsize(os.path.join(HERE, a + ".npz")))
         return
     gen_rpn()
+    gen_detect()
     feats, rois = gen_roi_align(ref)
     gen_pooler(feats, rois)
     gen_levels()

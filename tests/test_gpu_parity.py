@@ -731,3 +731,60 @@ def test_rpn_postprocessor_vs_oracle(training):
         assert len(bl) == rb.shape[0]
         assert np.array_equal(bl.get_field("objectness").cpu().numpy(), rs)
         np.testing.assert_allclose(bl.bbox.cpu().numpy(), rb, rtol=1e-5, atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# next row: detection post-processing around ml_nms, batched over images
+# ----------------------------------------------------------------------------------------------------------------
+def test_cls_postprocessor_golden(golden):
+    """The reference's CLSPostProcessor.forward outputs (tests/golden/detect.npz): same detections per image (one image
+    has no proposals), labels exact, scores to softmax rounding, order by decreasing score; and the rescoring branch."""
+    g = golden("detect")
+    counts = g["counts"].tolist()
+    img = tuple(int(v) for v in g["img_wh"])
+    pp = ops.CLSPostProcessor(float(g["params"][0]), float(g["params"][1]))
+    res = pp(cuda(g["logits"]), [ops.BoxList(cuda(g["boxes%d" % i]).reshape(-1, 4), img) for i in range(len(counts))])
+    for i, bl in enumerate(res):
+        rb, rs, rl = g["res_boxes%d" % i], g["res_scores%d" % i], g["res_labels%d" % i]
+        assert len(bl) == rb.shape[0]
+        assert np.array_equal(bl.get_field("labels").cpu().numpy(), rl)
+        np.testing.assert_allclose(bl.get_field("scores").cpu().numpy(), rs, rtol=2e-6, atol=1e-8)
+        assert np.array_equal(bl.bbox.cpu().numpy(), rb)
+    bl = ops.BoxList(cuda(g["boxes0"]), img)
+    bl.add_field("scores", cuda(g["rescore_in_scores"]))
+    bl.add_field("labels", cuda(g["rescore_in_labels"]))
+    out = pp(cuda(g["rescore_logits"]), [bl], rescore=True)
+    np.testing.assert_allclose(out[0].get_field("scores").cpu().numpy(), g["rescore_out"], rtol=1e-5, atol=1e-8)
+
+
+def test_cls_postprocessor_vs_oracle_batch():
+    """16 images x 1000 proposals x 81 classes (configs[2]'s detection flavour): one batched launch against the per-image
+    oracle fed with the same device softmax values; and against the reference's own `_C.ml_nms` per image when built."""
+    from oracle import detect
+    gen = torch.Generator().manual_seed(123)
+    B, R, C, img = 16, 1000, 81, (1344, 800)
+    boxes = [synthetic.coco_like_boxes(gen, R) for _ in range(B)]
+    logits = torch.randn(B * R, C, generator=gen)
+    pp = ops.CLSPostProcessor(0.03, 0.3)
+    l0 = ops.launch_count()
+    res = pp(logits.cuda(), [ops.BoxList(b.cuda(), img) for b in boxes])
+    assert ops.launch_count() - l0 <= 16
+    prob = torch.softmax(logits.cuda(), -1).cpu().numpy()
+    ref = detect.cls_postprocess(prob, [b.numpy() for b in boxes], [img] * B, 0.03, 0.3)
+    for bl, (rb, rs, rl) in zip(res, ref):
+        assert len(bl) == len(rs)
+        assert np.array_equal(bl.get_field("scores").cpu().numpy(), rs)
+        assert np.array_equal(bl.get_field("labels").cpu().numpy(), rl)
+        assert np.array_equal(bl.bbox.cpu().numpy(), rb)
+    try:
+        from oracle import build_ref
+        refk = build_ref.load("pet_ref_cuda")
+    except Exception:
+        return
+    # the reference kernel itself on image 0's candidates
+    p0 = torch.softmax(logits[:R].cuda(), -1)
+    m = p0 > 0.03
+    m[:, 0] = False
+    nz = m.nonzero()
+    keep = refk.ml_nms(boxes[0].cuda()[nz[:, 0]], p0[m], nz[:, 1].contiguous(), 0.3, 0)
+    assert torch.equal(p0[m][keep], res[0].get_field("scores"))

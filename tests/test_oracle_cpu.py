@@ -150,3 +150,19 @@ def test_rpn_selection_oracle_matches_reference(golden, tag):
         assert b.shape == rb.shape
         assert np.array_equal(s, rs)
         np.testing.assert_allclose(b, rb, rtol=2e-6, atol=2e-4)
+
+
+def test_detection_postprocess_oracle_matches_reference(golden):
+    """oracle/detect.py against the reference's CLSPostProcessor.forward run on CPU (tests/golden/detect.npz; the
+    softmax is torch's, the reference's own op, so the Python around the NMS is pinned bit for bit)."""
+    from oracle import detect
+    g = golden("detect")
+    counts = g["counts"].tolist()
+    img = tuple(int(v) for v in g["img_wh"])
+    prob = torch.softmax(torch.from_numpy(g["logits"]), -1).numpy()
+    res = detect.cls_postprocess(prob, [g["boxes%d" % i] for i in range(len(counts))], [img] * len(counts),
+                                 float(g["params"][0]), float(g["params"][1]))
+    for i, (b, s, l) in enumerate(res):
+        assert np.array_equal(b, g["res_boxes%d" % i])
+        assert np.array_equal(s, g["res_scores%d" % i])
+        assert np.array_equal(l, g["res_labels%d" % i])
