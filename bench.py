@@ -383,6 +383,7 @@ def run_ours(args):
     decode = bench_decode(ops, dev, rank)
     rpn = bench_rpn(ops, dev, rank)
     det = bench_detect(ops, dev, rank)
+    gtg = bench_grid_targets(ops, dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -419,7 +420,7 @@ def run_ours(args):
                                                           if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det}
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det, "grid_targets": gtg}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -620,6 +621,49 @@ def bench_detect(ops, dev, rank, iters=5):
     res["detections"] = sum(len(b) for b in ours())
     res["same_count_as_reference"] = res["detections"] == sum(reference_loop())
     res["speedup"] = res["reference_gpu_loop"]["ms"] / res["ours"]["ms"]
+    return res
+
+
+def bench_grid_targets(ops, dev, rank, iters=20):
+    """Next row: grid-point training targets for 2 x 96 positives (MAX_SAMPLE_NUM_GRID), stage 0.
+    Ours = one kernel writing (R,9,28,28) on the device (bytes = R*9*28*28*4 + 32R); cpu_baseline = the reference's
+    algorithm on the host (oracle port of the Python triple loop, loss.py:214-237) plus the upload of its result, which
+    is what the reference does every iteration and stage (:256-257)."""
+    from cpm_r_cnn_b200 import synthetic as sy
+    res = {}
+    if rank != 0:
+        return res
+    gen = torch.Generator().manual_seed(3)
+    R = 192
+    pos = sy.coco_like_boxes(gen, R)
+    gt = pos + (torch.rand(R, 4, generator=gen) - 0.5) * (pos[:, 2:] - pos[:, :2]).repeat(1, 2) * 0.6
+    pd, gd = pos.to(dev), gt.to(dev)
+    for _ in range(3):
+        ops.prepare_grid_target(pd, gd, 1.0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        t = ops.prepare_grid_target(pd, gd, 1.0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = R * 9 * 28 * 28 * 4 + 32 * R
+    res["ours"] = {"ms": ms, "rois_per_sec": R / (ms * 1e-3), "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9}
+    try:
+        import oracle
+        from oracle import grid_targets as ogt
+        sub = oracle.calc_sub_regions(9, 3, 56)
+        t0 = time.perf_counter()
+        ref = ogt.prepare_target(pos.numpy(), gt.numpy(), 1.0, sub)
+        up = torch.from_numpy(ref).to(dev)
+        torch.cuda.synchronize()
+        cms = (time.perf_counter() - t0) * 1e3
+        res["cpu_baseline"] = {"ms": cms, "rois_per_sec": R / (cms * 1e-3), "kind": "port", "cores": 1,
+                               "identical": bool(torch.equal(up, t))}
+        res["speedup"] = cms / ms
+    except Exception as ex:
+        res["cpu_baseline"] = {"unavailable": repr(ex)[:200]}
     return res
 
 

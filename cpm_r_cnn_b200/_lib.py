@@ -74,6 +74,9 @@ _SIGNATURES = {
     "cpm_rpn_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "cpm_grid_targets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int32), ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -208,6 +208,15 @@ CPM_API int cpm_rpn_decode(const float* d_deltas, const float* d_anchors, const 
                    const float* weights, float bbox_xform_clip, float min_size, float* d_boxes, int32_t* d_segments_out,
                    void* stream);
 
+/* ---- grid-point training targets (next row) ------------------------------------
+ * Replaces GridLossComputation.prepare_target (grid_cascade_rcnn/loss.py:178-258: CPU triple loop + H2D).
+ *   d_pos_boxes, d_gt_boxes (R,4) fp32: positive RoIs and their matched ground truth; sub_xy = HOST int32[P*2] sub-region
+ *   offsets (calc_sub_regions, grid_rcnn/loss.py:244-273); map_size = 4 * roi_feat_size (56);
+ *   d_targets (R, P, map_size/2, map_size/2) fp32 of 0/1, fully written. */
+CPM_API int cpm_grid_targets(const float* d_pos_boxes, const float* d_gt_boxes, int64_t R, int grid_points, int map_size,
+                     const int32_t* sub_xy, float mapping_ratio, int pos_radius, int target_refine, float* d_targets,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

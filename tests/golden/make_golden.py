@@ -304,18 +304,43 @@ def gen_detect():
     np.savez_compressed(os.path.join(HERE, "detect.npz"), **out)
 
 
+def gen_grid_targets():
+    """GridLossComputation.prepare_target (grid_cascade_rcnn/loss.py:178-258) for the three cascade stages, on boxes
+    that include tiny RoIs (skipped), ground truth far outside the extended RoI (disks clipped / off the map) and exact
+    half-pixel cases."""
+    from pet.rcnn.modeling.grid_cascade_rcnn.loss import GridLossComputation
+    g = torch.Generator().manual_seed(7)
+    R = 48
+    pos = coco_like_rois(g, R - 8, 800, 1344, 1)[:R, 1:].clone()
+    jitter = (torch.rand(R, 4, generator=g) - 0.5) * (pos[:, 2:] - pos[:, :2]).repeat(1, 2) * 0.5
+    gt = pos + jitter
+    pos[5] = torch.tensor([100.0, 100.0, 102.0, 140.0])      # narrower than the grid -> ignored
+    gt[9] = pos[9] + 400.0                                    # ground truth far away: disks off the map
+    gt[11] = pos[11].clone()                                  # identical boxes
+    out = {"pos": pos.numpy(), "gt": gt.numpy()}
+    for stage in range(3):
+        lc = GridLossComputation(stage, 1.0, None, 1, 9, 14)
+        lc.pos_result = (pos.clone(), gt.clone())
+        out["stage%d" % stage] = lc.prepare_target(None, None).numpy().astype(np.uint8)
+    lc = GridLossComputation(0, 1.0, None, 2, 9, 14)
+    lc.pos_result = (pos.clone(), gt.clone())
+    out["radius2"] = lc.prepare_target(None, None).numpy().astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "grid_targets.npz"), **out)
+
+
 def main():
     build_ref.build(cuda=False)
     ref = build_ref.load("pet_ref_cpu")
     install_shims(ref)
-    only = [a for a in sys.argv[1:] if a in ("rpn", "detect")]
+    only = [a for a in sys.argv[1:] if a in ("rpn", "detect", "grid_targets")]
     if only:
         for a in only:
-            {"rpn": gen_rpn, "detect": gen_detect}[a]()
+            {"rpn": gen_rpn, "detect": gen_detect, "grid_targets": gen_grid_targets}[a]()
             print(a + ".npz", os.path.getsize(os.path.join(HERE, a + ".npz")))
         return
     gen_rpn()
     gen_detect()
+    gen_grid_targets()
     feats, rois = gen_roi_align(ref)
     gen_pooler(feats, rois)
     gen_levels()

@@ -788,3 +788,39 @@ def test_cls_postprocessor_vs_oracle_batch():
     nz = m.nonzero()
     keep = refk.ml_nms(boxes[0].cuda()[nz[:, 0]], p0[m], nz[:, 1].contiguous(), 0.3, 0)
     assert torch.equal(p0[m][keep], res[0].get_field("scores"))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# next row: grid-point training targets rasterised on the device
+# ----------------------------------------------------------------------------------------------------------------
+def test_grid_targets_golden(golden):
+    """Bit-exact 0/1 maps against the reference's prepare_target (tests/golden/grid_targets.npz), all three stages."""
+    g = golden("grid_targets")
+    pos, gt = cuda(g["pos"]), cuda(g["gt"])
+    for stage in range(3):
+        t = ops.GridTargetGenerator(stage).prepare_target(pos, gt)
+        assert t.dtype == torch.float32 and t.shape == (pos.shape[0], 9, 28, 28)
+        assert np.array_equal(t.cpu().numpy().astype(np.uint8), g["stage%d" % stage])
+    t = ops.prepare_grid_target(pos, gt, 1.0, pos_radius=2)
+    assert np.array_equal(t.cpu().numpy().astype(np.uint8), g["radius2"])
+    assert ops.prepare_grid_target(pos[:0], gt[:0], 1.0).shape == (0, 9, 28, 28)
+    with pytest.raises(RuntimeError):
+        ops.prepare_grid_target(pos.cpu(), gt.cpu(), 1.0)
+
+
+def test_grid_targets_random_vs_oracle():
+    """MAX_SAMPLE_NUM_GRID-sized batch (2 x 96 positives), ground truth jittered around the RoI incl. far outliers,
+    TARGET_REFINE on and off, a 4x4 grid: identical maps to the numpy restatement of the reference loop."""
+    from oracle import grid_targets as ogt
+    gen = torch.Generator().manual_seed(55)
+    R = 192
+    pos = synthetic.coco_like_boxes(gen, R)
+    gt = pos + (torch.rand(R, 4, generator=gen) - 0.5) * (pos[:, 2:] - pos[:, :2]).repeat(1, 2) * 1.5
+    for ratio, refine, points, radius in ((1.0, False, 9, 1), (0.25, True, 9, 1), (0.5, True, 16, 2)):
+        gs = int(round(points ** 0.5))
+        sub = oracle.calc_sub_regions(points, gs, 56)
+        ref = ogt.prepare_target(pos.numpy(), gt.numpy(), ratio, sub, pos_radius=radius, grid_points=points,
+                                 target_refine=refine)
+        out = ops.prepare_grid_target(pos.cuda(), gt.cuda(), ratio, pos_radius=radius, grid_points=points,
+                                      target_refine=refine)
+        assert np.array_equal(out.cpu().numpy(), ref)

@@ -166,3 +166,15 @@ def test_detection_postprocess_oracle_matches_reference(golden):
         assert np.array_equal(b, g["res_boxes%d" % i])
         assert np.array_equal(s, g["res_scores%d" % i])
         assert np.array_equal(l, g["res_labels%d" % i])
+
+
+def test_grid_targets_oracle_matches_reference(golden):
+    """oracle/grid_targets.py against GridLossComputation.prepare_target run on CPU (tests/golden/grid_targets.npz):
+    the 0/1 maps are identical for the three cascade stages and for radius 2."""
+    from oracle import grid_targets as ogt
+    g = golden("grid_targets")
+    sub = oracle.calc_sub_regions(9, 3, 56)
+    for stage, ratio in enumerate((1.0, 0.5, 0.25)):
+        t = ogt.prepare_target(g["pos"], g["gt"], ratio, sub)
+        assert np.array_equal(t.astype(np.uint8), g["stage%d" % stage])
+    assert np.array_equal(ogt.prepare_target(g["pos"], g["gt"], 1.0, sub, pos_radius=2).astype(np.uint8), g["radius2"])
