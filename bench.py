@@ -202,9 +202,13 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: the cpm_ops path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one line, the JSON: everything libraries print while the job runs (NCCL writes its version
+    # banner to stdout when the first communicator is created) is routed to stderr, and the real stdout is restored for
+    # the result
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
@@ -424,7 +428,10 @@ def run_ours(args):
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
