@@ -29,11 +29,12 @@ class CLSPostProcessor(nn.Module):
         rescore=True is the reference's rescoring branch (:62-76): scores <- scores^0.8 * prob[label]^0.2 in place."""
         class_prob = F.softmax(x, -1)
         if rescore:
-            for boxes_per_image in boxes:
-                rescores = class_prob[torch.arange(class_prob.shape[0], device=class_prob.device),
-                                      boxes_per_image.get_field("labels")]
-                rescores = (boxes_per_image.get_field("scores") ** 0.8) * (rescores ** 0.2)
-                boxes_per_image.add_field("scores", rescores)
+            # :62-76 -- the geometric blend of the detection score with the rescoring head's probability of its label
+            # (weights 0.8 / 0.2, 'pow' mode); every BoxList indexes the full probability table, as in the reference
+            rows = torch.arange(class_prob.shape[0], device=class_prob.device)
+            for bl in boxes:
+                p_label = class_prob[rows, bl.get_field("labels")]
+                bl.add_field("scores", bl.get_field("scores").pow(0.8) * p_label.pow(0.2))
             return boxes
         _lib.require_cuda(x, "class logits")
         dev = x.device

@@ -87,16 +87,16 @@ class RPNPostProcessor(nn.Module):
         return out
 
     def _level_candidates(self, anchors, objectness, box_regression):
-        """inference.py:75-94, unchanged: sigmoid, per-image top-k, gather of deltas and anchors (all torch, batched)."""
+        """One FPN level, all images at once (what inference.py:75-94 computes): objectness probabilities of the
+        pre_nms_top_n best anchors per image, with their regression deltas and anchor boxes."""
         N, A, H, W = objectness.shape
-        objectness = permute_and_flatten(objectness, N, A, 1, H, W).view(N, -1).sigmoid()
-        box_regression = permute_and_flatten(box_regression, N, A, 4, H, W)
-        pre_nms_top_n = min(self.pre_nms_top_n, A * H * W)
-        objectness, topk_idx = objectness.topk(pre_nms_top_n, dim=1, sorted=True)
-        batch_idx = torch.arange(N, device=objectness.device)[:, None]
-        box_regression = box_regression[batch_idx, topk_idx]
-        concat_anchors = torch.cat([a.bbox for a in anchors], dim=0).reshape(N, -1, 4)[batch_idx, topk_idx]
-        return objectness, box_regression, concat_anchors
+        k = min(self.pre_nms_top_n, A * H * W)
+        prob = permute_and_flatten(objectness, N, A, 1, H, W).view(N, -1).sigmoid()
+        top_prob, top_idx = prob.topk(k, dim=1, sorted=True)
+        pick = top_idx.unsqueeze(-1).expand(N, k, 4)
+        deltas = permute_and_flatten(box_regression, N, A, 4, H, W).gather(1, pick)
+        level_anchors = torch.cat([a.bbox for a in anchors], dim=0).reshape(N, -1, 4).gather(1, pick)
+        return top_prob, deltas, level_anchors
 
     def forward(self, anchors, objectness, box_regression, targets=None):
         """anchors: list (images) of list (levels) of BoxList; objectness / box_regression: list (levels) of tensors
@@ -138,22 +138,14 @@ class RPNPostProcessor(nn.Module):
         return boxlists
 
     def select_over_all_levels(self, boxlists):
-        """inference.py:145-172: training = top-k over the whole batch (Detectron convention), testing = per image."""
-        num_images = len(boxlists)
+        """inference.py:145-172.  Training (with fpn_post_nms_per_batch, the Detectron convention): the
+        fpn_post_nms_top_n best proposals of the WHOLE batch survive, each image keeps its own in their current order.
+        Testing: every image keeps its fpn_post_nms_top_n best, ordered by decreasing objectness."""
+        scores = [b.get_field("objectness") for b in boxlists]
         if self.training and self.fpn_post_nms_per_batch:
-            objectness = torch.cat([b.get_field("objectness") for b in boxlists], dim=0)
-            box_sizes = [len(b) for b in boxlists]
-            post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
-            _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
-            inds_mask = torch.zeros_like(objectness, dtype=torch.bool)
-            inds_mask[inds_sorted] = 1
-            inds_mask = inds_mask.split(box_sizes)
-            for i in range(num_images):
-                boxlists[i] = boxlists[i][inds_mask[i]]
-        else:
-            for i in range(num_images):
-                objectness = boxlists[i].get_field("objectness")
-                post_nms_top_n = min(self.fpn_post_nms_top_n, len(objectness))
-                _, inds_sorted = torch.topk(objectness, post_nms_top_n, dim=0, sorted=True)
-                boxlists[i] = boxlists[i][inds_sorted]
-        return boxlists
+            flat = torch.cat(scores, dim=0)
+            chosen = torch.zeros_like(flat, dtype=torch.bool)
+            chosen[flat.topk(min(self.fpn_post_nms_top_n, flat.numel()), dim=0, sorted=True).indices] = True
+            return [b[m] for b, m in zip(boxlists, chosen.split([len(b) for b in boxlists]))]
+        return [b[s.topk(min(self.fpn_post_nms_top_n, s.numel()), dim=0, sorted=True).indices]
+                for b, s in zip(boxlists, scores)]
