@@ -388,6 +388,7 @@ def run_ours(args):
     rpn = bench_rpn(ops, dev, rank)
     det = bench_detect(ops, dev, rank)
     gtg = bench_grid_targets(ops, dev, rank)
+    mat = bench_matcher(ops, dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -424,7 +425,7 @@ def run_ours(args):
                                                           if "error" not in cl_ms else cl_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det, "grid_targets": gtg}
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det, "grid_targets": gtg, "iou_matcher": mat}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -671,6 +672,55 @@ def bench_grid_targets(ops, dev, rank, iters=20):
         res["speedup"] = cms / ms
     except Exception as ex:
         res["cpu_baseline"] = {"unavailable": repr(ex)[:200]}
+    return res
+
+
+def bench_matcher(ops, dev, rank, iters=20):
+    """Next row: IoU matrix + Matcher for one image, 50 ground-truth boxes x 2000 proposals (RPN
+    thresholds, low-quality matches on).  Ours = cpm_box_iou + cpm_matcher (3 launches, no host sync); reference_gpu = the
+    reference's torch expressions (boxlist_ops.py:123-158, matcher.py:52-112) on the same GPU."""
+    from cpm_r_cnn_b200 import synthetic as sy
+    res = {}
+    if rank != 0:
+        return res
+    gen = torch.Generator().manual_seed(12)
+    M, N, img = 50, 2000, (sy.IMG_W, sy.IMG_H)
+    gt, pr = sy.coco_like_boxes(gen, M).to(dev), sy.coco_like_boxes(gen, N).to(dev)
+    g, p = ops.BoxList(gt, img), ops.BoxList(pr, img)
+    matcher = ops.Matcher(0.7, 0.3, True)
+
+    def ours():
+        return matcher(ops.boxlist_iou(g, p))
+
+    def reference():
+        a1 = (gt[:, 2] - gt[:, 0] + 1) * (gt[:, 3] - gt[:, 1] + 1)
+        a2 = (pr[:, 2] - pr[:, 0] + 1) * (pr[:, 3] - pr[:, 1] + 1)
+        lt, rb = torch.max(gt[:, None, :2], pr[:, :2]), torch.min(gt[:, None, 2:], pr[:, 2:])
+        wh = (rb - lt + 1).clamp(min=0)
+        inter = wh[:, :, 0] * wh[:, :, 1]
+        q = inter / (a1[:, None] + a2 - inter)
+        vals, m = q.max(dim=0)
+        allm = m.clone()
+        m[vals < 0.3] = -1
+        m[(vals >= 0.3) & (vals < 0.7)] = -2
+        best, _ = q.max(dim=1)
+        upd = torch.nonzero(q == best[:, None])[:, 1]
+        m[upd] = allm[upd]
+        return m
+
+    same = bool(torch.equal(ours(), reference()))
+    for name, fn in (("ours", ours), ("reference_gpu", reference)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / iters
+        res[name] = {"ms": ms, "pairs_per_sec": M * N / (ms * 1e-3)}
+    res["identical"] = same
+    res["speedup"] = res["reference_gpu"]["ms"] / res["ours"]["ms"]
     return res
 
 

@@ -13,6 +13,7 @@ from .boxlist_ops import (batched_boxlist_nms, boxlist_ml_nms, boxlist_ml_nms_le
 from .detect_postprocess import CLSPostProcessor
 from .grid_decode import GridPostProcessor, calc_sub_regions, grid_decode
 from .grid_targets import GridTargetGenerator, prepare_grid_target
+from .matcher import Matcher, boxlist_iou
 from .nms import batched_nms, ml_nms, nms
 from .poolers import LevelMapper, Pooler
 from .roi_align import ROIAlign, roi_align, stage_nhwc
@@ -22,4 +23,4 @@ from .structures import BoxList
 __all__ = ["ROIAlign", "roi_align", "stage_nhwc", "nms", "ml_nms", "batched_nms", "boxlist_nms", "boxlist_ml_nms",
            "boxlist_nms_legacy", "boxlist_ml_nms_legacy", "batched_boxlist_nms", "Pooler", "LevelMapper",
            "grid_decode", "calc_sub_regions", "GridPostProcessor", "BoxList", "launch_count", "RPNPostProcessor", "BoxCoder",
-           "rpn_decode", "CLSPostProcessor", "GridTargetGenerator", "prepare_grid_target"]
+           "rpn_decode", "CLSPostProcessor", "GridTargetGenerator", "prepare_grid_target", "Matcher", "boxlist_iou"]

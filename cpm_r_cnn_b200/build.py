@@ -16,7 +16,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcpm_ops.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_bwd.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "layout.cu"]
+SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_bwd.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "matcher.cu", "layout.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "cpm_ops.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

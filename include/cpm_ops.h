@@ -217,6 +217,17 @@ CPM_API int cpm_grid_targets(const float* d_pos_boxes, const float* d_gt_boxes, 
                      const int32_t* sub_xy, float mapping_ratio, int pos_radius, int target_refine, float* d_targets,
                      void* stream);
 
+/* ---- box IoU matrix + Matcher (next row) ----------------------------------------
+ * cpm_box_iou: boxlist_iou (pet/utils/data/structures/boxlist_ops.py:123-158): d_iou (N,M) = IoU with the +1 area
+ *   convention of boxes1 (N,4) against boxes2 (M,4), fp32, the reference's operation order.
+ * cpm_matcher: Matcher.__call__ (pet/rcnn/utils/matcher.py:52-112) on an (M,N) quality matrix (M ground truth x N
+ *   predictions): d_matches int64[N] = index of the best ground truth, -1 below low_threshold, -2 between the thresholds;
+ *   allow_low_quality_matches restores every prediction that ties some ground truth's best overlap.  No host sync. */
+CPM_API int cpm_box_iou(const float* d_boxes1, const float* d_boxes2, int64_t N, int64_t M, float* d_iou, void* stream);
+CPM_API size_t cpm_matcher_workspace_bytes(int64_t M, int64_t N);
+CPM_API int cpm_matcher(const float* d_quality, int64_t M, int64_t N, float high_threshold, float low_threshold,
+                int allow_low_quality_matches, int64_t* d_matches, void* d_workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

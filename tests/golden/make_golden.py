@@ -328,19 +328,42 @@ def gen_grid_targets():
     np.savez_compressed(os.path.join(HERE, "grid_targets.npz"), **out)
 
 
+def gen_matcher():
+    """boxlist_iou + Matcher (pet/utils/data/structures/boxlist_ops.py:123-158, pet/rcnn/utils/matcher.py) on CPU:
+    RPN thresholds with low-quality matches, head thresholds without; ground truth incl. a duplicate box (exact ties) and
+    a box that overlaps nothing."""
+    from pet.rcnn.utils.matcher import Matcher
+    from pet.utils.data.structures.bounding_box import BoxList
+    from pet.utils.data.structures.boxlist_ops import boxlist_iou
+    g = torch.Generator().manual_seed(31)
+    img = (1344, 800)
+    gt = coco_like_rois(g, 12, img[1], img[0], 1)[:12, 1:].clone()
+    gt[5] = gt[2]                                             # duplicate ground truth: ties in the column arg-max
+    gt[7] = torch.tensor([1300.0, 760.0, 1343.0, 799.0])
+    props = torch.cat([coco_like_rois(g, 600, img[1], img[0], 1)[:600, 1:],
+                       gt[:6] + (torch.rand(6, 4, generator=g) - 0.5) * 6, gt[2:4].clone()], 0)
+    q = boxlist_iou(BoxList(gt, img), BoxList(props, img))
+    out = {"gt": gt.numpy(), "props": props.numpy(), "iou": q.numpy()}
+    for tag, (hi, lo, allow) in {"rpn": (0.7, 0.3, True), "head": (0.5, 0.5, False), "grid": (0.5, 0.5, True)}.items():
+        out["match_" + tag] = Matcher(hi, lo, allow)(q.clone()).numpy()
+        out["params_" + tag] = np.array([hi, lo, float(allow)])
+    np.savez_compressed(os.path.join(HERE, "matcher.npz"), **out)
+
+
 def main():
     build_ref.build(cuda=False)
     ref = build_ref.load("pet_ref_cpu")
     install_shims(ref)
-    only = [a for a in sys.argv[1:] if a in ("rpn", "detect", "grid_targets")]
+    only = [a for a in sys.argv[1:] if a in ("rpn", "detect", "grid_targets", "matcher")]
     if only:
         for a in only:
-            {"rpn": gen_rpn, "detect": gen_detect, "grid_targets": gen_grid_targets}[a]()
+            {"rpn": gen_rpn, "detect": gen_detect, "grid_targets": gen_grid_targets, "matcher": gen_matcher}[a]()
             print(a + ".npz", os.path.getsize(os.path.join(HERE, a + ".npz")))
         return
     gen_rpn()
     gen_detect()
     gen_grid_targets()
+    gen_matcher()
     feats, rois = gen_roi_align(ref)
     gen_pooler(feats, rois)
     gen_levels()

@@ -824,3 +824,36 @@ def test_grid_targets_random_vs_oracle():
         out = ops.prepare_grid_target(pos.cuda(), gt.cuda(), ratio, pos_radius=radius, grid_points=points,
                                       target_refine=refine)
         assert np.array_equal(out.cpu().numpy(), ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# next row: box IoU matrix + Matcher on the device
+# ----------------------------------------------------------------------------------------------------------------
+def test_iou_and_matcher_golden(golden):
+    """Bit-identical to the reference's boxlist_iou and Matcher (tests/golden/matcher.npz), incl. duplicate ground truth
+    (first-index arg-max), a ground truth that overlaps nothing, and both low-quality settings."""
+    g = golden("matcher")
+    img = (1344, 800)
+    q = ops.boxlist_iou(ops.BoxList(cuda(g["gt"]), img), ops.BoxList(cuda(g["props"]), img))
+    assert np.array_equal(q.cpu().numpy(), g["iou"])
+    for tag in ("rpn", "head", "grid"):
+        hi, lo, allow = g["params_" + tag]
+        m = ops.Matcher(float(hi), float(lo), bool(allow))(q)
+        assert m.dtype == torch.int64 and np.array_equal(m.cpu().numpy(), g["match_" + tag])
+    with pytest.raises(ValueError):
+        ops.Matcher(0.5, 0.5)(q[:0])
+    with pytest.raises(RuntimeError):
+        ops.boxlist_iou(ops.BoxList(cuda(g["gt"]), img), ops.BoxList(cuda(g["props"]), (10, 10)))
+
+
+def test_iou_and_matcher_random_vs_oracle():
+    from oracle import matcher as om
+    gen = torch.Generator().manual_seed(64)
+    for M, N in ((1, 1), (3, 2000), (100, 2503), (40, 33)):
+        gt, pr = synthetic.coco_like_boxes(gen, M), synthetic.coco_like_boxes(gen, N)
+        pr[::7] = gt[torch.randint(0, M, (len(pr[::7]),), generator=gen)]           # exact duplicates -> IoU 1 ties
+        q = ops.boxlist_iou(ops.BoxList(gt.cuda(), (1344, 800)), ops.BoxList(pr.cuda(), (1344, 800)))
+        ref = om.box_iou(gt.numpy(), pr.numpy())
+        assert np.array_equal(q.cpu().numpy(), ref)
+        for hi, lo, allow in ((0.7, 0.3, True), (0.5, 0.5, False), (0.5, 0.1, True)):
+            assert np.array_equal(ops.Matcher(hi, lo, allow)(q).cpu().numpy(), om.match(ref, hi, lo, allow))

@@ -178,3 +178,15 @@ def test_grid_targets_oracle_matches_reference(golden):
         t = ogt.prepare_target(g["pos"], g["gt"], ratio, sub)
         assert np.array_equal(t.astype(np.uint8), g["stage%d" % stage])
     assert np.array_equal(ogt.prepare_target(g["pos"], g["gt"], 1.0, sub, pos_radius=2).astype(np.uint8), g["radius2"])
+
+
+def test_iou_and_matcher_oracle_match_reference(golden):
+    """oracle/matcher.py against the reference's boxlist_iou + Matcher run on CPU (tests/golden/matcher.npz): the IoU
+    matrix and the three match vectors are bit-identical."""
+    from oracle import matcher as om
+    g = golden("matcher")
+    q = om.box_iou(g["gt"], g["props"])
+    assert np.array_equal(q, g["iou"])
+    for tag in ("rpn", "head", "grid"):
+        hi, lo, allow = g["params_" + tag]
+        assert np.array_equal(om.match(g["iou"], hi, lo, bool(allow)), g["match_" + tag])
