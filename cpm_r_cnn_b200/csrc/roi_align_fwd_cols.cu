@@ -270,7 +270,7 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   const bool ok = l >= 0 && l < pv.num_levels && geo.b >= 0 && geo.b < pv.batch;
   constexpr int kTileFloats = OCL ? 0 : CH * PP + SK * (CH / 4);      // a channels-last output needs no staging tile
   constexpr int kTileBytes = (kTileFloats * 4 + 15) & ~15;
-  const bool store_issuer = NG == 1 ? threadIdx.x == 0 : threadIdx.x < CH;      // threads that own bulk-store groups
+  const bool store_issuer = NG == 1 ? threadIdx.x == 0 : threadIdx.x < CH / 4;  // threads that own bulk-store groups
   // tile -> out[n, c0 : c0 + CH, :, :], asynchronous: the next chunk's column loop runs while the tile drains
   auto store_tile = [&](int c0) {
     if (OCL) return;
@@ -283,9 +283,9 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
         bulk_commit();
       }
     } else {
-      if (threadIdx.x < CH) {
-        const int c = threadIdx.x;
-        bulk_s2g(o + (size_t)c * PP, tile + c * PP + SK * (c >> 2), PP * 4);
+      if (threadIdx.x < CH / 4) {      // the skew sits between groups of 4 channels: one 3 136-byte store per group
+        const int c4 = threadIdx.x;
+        bulk_s2g(o + (size_t)c4 * 4 * PP, tile + c4 * (4 * PP + SK), 4 * PP * 4);
         bulk_commit();
       }
     }
