@@ -98,11 +98,10 @@ class Pooler(nn.Module):
 
     def convert_to_roi_format(self, boxes):
         """poolers.py:90-101: (K,5) [image index, x1, y1, x2, y2] in the boxes' dtype."""
-        concat_boxes = torch.cat([b.bbox for b in boxes], dim=0)
-        counts = torch.tensor([len(b) for b in boxes], dtype=torch.int64)
-        ids = torch.repeat_interleave(torch.arange(len(boxes), dtype=concat_boxes.dtype), counts)
-        ids = ids.to(concat_boxes.device, non_blocking=True)
-        return torch.cat([ids[:, None], concat_boxes], dim=1)
+        # built on the boxes' device with fill kernels only: a host->device copy here, however small, queues behind
+        # whatever large upload the caller has in flight on the copy engine and stalls the pooler
+        return torch.cat([torch.cat([b.bbox.new_full((len(b), 1), float(i)), b.bbox], dim=1) for i, b in enumerate(boxes)],
+                         dim=0)
 
     def forward(self, x, boxes):
         """x: list[Tensor] feature maps (one per level, extra levels are ignored like zip() does at poolers.py:127);
