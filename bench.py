@@ -325,6 +325,39 @@ def run_ours(args):
         cl_ms = {"error": repr(ex)[:200]}
     sync_all()
 
+    # ---- the red.global.add fallback of the backward (non-deterministic order), reported separately ----
+    atomic_ms = {}
+    try:
+        at_fns = [(lambda p=p, go=go: pooler_backward(go, shapes, scales, rois, p, SAMPLING, False, 0, mapper, mode="atomic"))
+                  for p, go in zip(POOLERS, gouts)]
+        with torch.cuda.stream(side):
+            for fn in at_fns:
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        sync_all()
+        at_graphs, at_keep = [], []
+        for fn in at_fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                at_keep.append(fn())
+            at_graphs.append(g)
+        acc = [0.0, 0.0]
+        for it in range(7):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            for j, g in enumerate(at_graphs):
+                e[j].record()
+                g.replay()
+            e[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                acc[0] += e[0].elapsed_time(e[1])
+                acc[1] += e[1].elapsed_time(e[2])
+        atomic_ms = {"bwd7": acc[0] / 5, "bwd14": acc[1] / 5}
+        del at_graphs, at_keep
+    except Exception as ex:
+        atomic_ms = {"error": repr(ex)[:200]}
+    sync_all()
+
     # ---- e2e: host (pinned) buffers in and out, copies inside the timed region ----
     # One step = H2D of the pyramid, the RoIs and both pooled gradients, the two Pooler modules forward + one autograd
     # backward (the feature gradient of both poolers accumulates into x.grad, as in the head), D2H of both pooled outputs
@@ -432,6 +465,7 @@ def run_ours(args):
                              "step": {"bytes": total_bytes, "gbs": total_bytes / (ms_step * 1e-3) / 1e9,
                                       "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
                              "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]},
+                             "backward_atomic_fallback_ms": atomic_ms,
                              "ops_channels_last_pooled": ({n: {"ms": cl_ms[n], "gbs": ab[n] / (cl_ms[n] * 1e-3) / 1e9,
                                                                "frac": ab[n] / (cl_ms[n] * 1e-3) / 1e9 / peak} for n in names}
                                                           if "error" not in cl_ms else cl_ms)},
