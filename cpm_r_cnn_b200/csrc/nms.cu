@@ -79,11 +79,15 @@ __global__ void nms_gather(const float* __restrict__ boxes, const unsigned long 
   heads[i] = i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32);
 }
 
-constexpr int kSweepThreads = 256;
 constexpr int kSweepCap = 2048;         // boxes of a segment kept in shared memory (larger segments read global/L2)
 constexpr int kSweepMaxSeg = 65536;     // suppression bits of one segment live in shared memory
 
-__global__ void __launch_bounds__(kSweepThreads) nms_sweep(const float4* __restrict__ sboxes, const int* __restrict__ starts,
+// WIDE = false: 256 threads, the phase's 64 rows resolved from registers by one thread -- many resident CTAs, for many
+//               segments (detection: image x class).
+// WIDE = true : 1024 threads on the strip test, rows resolved by one warp with shuffles -- for few large segments (RPN:
+//               image x level with ~1000 boxes each), where one CTA per segment leaves most of the machine idle.
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* __restrict__ sboxes, const int* __restrict__ starts,
                                                             const int* __restrict__ d_nseg, int N,
                                                             const unsigned long long* __restrict__ keys, float thr,
                                                             long long topk, int flavor, unsigned char* __restrict__ flags,
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const float4* __restr
   __shared__ unsigned long long s_kept;
   __shared__ int s_done;
   const int tid = threadIdx.x;
+  constexpr int kSweepThreads = WIDE ? 1024 : 256;
   const int nseg = *d_nseg;
   for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
     const int beg = starts[s];
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const float4* __restr
       // ---- 64x64 IoU bit-matrix of this phase: thread t -> row t/4, 16 columns ----
       if (tid < 64) diag[tid] = 0ull;
       __syncthreads();
-      {
+      if (tid < 256) {
         const int i = tid >> 2, j0 = (tid & 3) * 16;
         if (i < m && !((rem[(base + i) >> 5] >> ((base + i) & 31)) & 1u)) {
           const float4 a = in_smem ? sb[base + i] : gb[base + i];
@@ -132,19 +137,30 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const float4* __restr
       }
       __syncthreads();
       // ---- serial resolve (ml_nms.cu:127-140 restricted to the phase), rows register-resident ----
-      if (tid == 0) {
-        unsigned long long row[64];
-#pragma unroll
-        for (int i = 0; i < 64; i++) row[i] = diag[i];
+      if (WIDE ? tid < 32 : tid == 0) {
         const unsigned lo = rem[base >> 5], hi = (base + 32 < n) ? rem[(base >> 5) + 1] : 0u;
         unsigned long long alive = ~(((unsigned long long)hi << 32) | lo);
         if (m < 64) alive &= (1ull << m) - 1;
         unsigned long long kept = 0ull;
+        if (WIDE) {       // lane l holds rows l and l + 32; the row of every kept box is broadcast (alive / kept are uniform)
+          const unsigned long long r0 = diag[tid & 31], r1 = diag[(tid & 31) + 32];
 #pragma unroll
-        for (int i = 0; i < 64; i++) {
-          if ((alive >> i) & 1ull) {
-            kept |= 1ull << i;
-            alive &= ~row[i];
+          for (int i = 0; i < 64; i++) {
+            if ((alive >> i) & 1ull) {
+              kept |= 1ull << i;
+              alive &= ~__shfl_sync(0xffffffffu, i < 32 ? r0 : r1, i & 31);
+            }
+          }
+        } else {
+          unsigned long long row[64];
+#pragma unroll
+          for (int i = 0; i < 64; i++) row[i] = diag[i];
+#pragma unroll
+          for (int i = 0; i < 64; i++) {
+            if ((alive >> i) & 1ull) {
+              kept |= 1ull << i;
+              alive &= ~row[i];
+            }
           }
         }
         int done = 0;
@@ -159,8 +175,10 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const float4* __restr
           kept = k2;
           done = 1;
         }
-        s_kept = kept;
-        s_done = done;
+        if (tid == 0) {
+          s_kept = kept;
+          s_done = done;
+        }
       }
       __syncthreads();
       const unsigned long long kept = s_kept;
@@ -326,10 +344,15 @@ static int run_nms(const float* d_boxes, const float* d_scores, const void* d_se
   cub_bytes = w.cub_bytes;
   CPM_CHECK_CUDA(cub::DeviceSelect::Flagged(cub_tmp, cub_bytes, cnt, heads, starts, d_nseg, n, st));
   count_launch(2);
-  int grid = 148 * 4;
-  if (mode == 0) grid = 1;
-  nms_sweep<<<grid, kSweepThreads, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, mode == 2 ? 0LL : (long long)topk,
-                                            flavor, flags, mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, d_err);
+  const int64_t segs = mode == 1 ? (num_segments > 0 ? num_segments : 1) : 1;
+  const bool wide = mode == 0 || (n / segs >= 256 && segs < 148 * 4);
+  if (wide)
+    nms_sweep<true><<<mode == 0 ? 1 : 148 * 2, 1024, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr,
+                                                              mode == 2 ? 0LL : (long long)topk, flavor, flags,
+                                                              mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, d_err);
+  else
+    nms_sweep<false><<<148 * 4, 256, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, mode == 2 ? 0LL : (long long)topk,
+                                              flavor, flags, mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, d_err);
   CPM_CHECK_LAUNCH();
   if (mode == 2) {
     nms_rekey<<<gb, tb, 0, st>>>(keys_b, vals_b, flags, n, keys_a);
