@@ -350,20 +350,99 @@ def gen_matcher():
     np.savez_compressed(os.path.join(HERE, "matcher.npz"), **out)
 
 
+def gen_grid_forward():
+    """GridPostProcessor.forward (inference.py:145-187): training (ground-truth rows filtered out, ground truth appended;
+    two images, one of them with every proposal equal to a ground truth) and testing (stage 0 on two images; last stage on
+    one image with the IoU head's score merge)."""
+    from pet.rcnn.modeling.grid_cascade_rcnn.inference import GridPostProcessor
+    from pet.utils.data.structures.bounding_box import BoxList
+    from pet.rcnn.core.config import cfg
+    torch.Tensor.get_device = lambda self: "cpu"
+    # the published CPM models' switches (SURVEY.md appendix A; e.g. the R-50 yaml lines 21-34)
+    cfg.GRID_RCNN.FUSED_ON = False
+    cfg.GRID_RCNN.IOU_HELPER = True
+    cfg.GRID_RCNN.IOU_HELPER_MERGE = True
+    g = torch.Generator().manual_seed(97531)
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * 400
+        wh = torch.rand(n, 2, generator=g) * 300 + 8
+        return torch.cat([xy, xy + wh], 1)
+
+    out = {}
+    # ---- training, stage 1
+    gts = [boxes(3), boxes(2)]
+    props = [torch.cat([boxes(5), gts[0][:2], boxes(1)[:, [0, 1, 2, 3]]], 0), gts[1].clone()]
+    props[0][6, 0] = gts[0][2, 0]                       # one coordinate equal to a ground truth's: kept (sum stays > 0)
+    counts = [p.shape[0] for p in props]
+    logits = torch.randn(sum(counts), 9, 28, 28, generator=g) * 2
+    bls, tgts = [], []
+    for p, t in zip(props, gts):
+        bl = BoxList(p.clone(), (1000, 800), mode="xyxy")
+        bl.add_field("labels", torch.randint(1, 81, (p.shape[0],), generator=g))
+        bl.add_field("objectness", torch.rand(p.shape[0], generator=g))
+        tl = BoxList(t.clone(), (1000, 800), mode="xyxy")
+        tl.add_field("labels", torch.randint(1, 81, (t.shape[0],), generator=g))
+        bls.append(bl)
+        tgts.append(tl)
+    out["train_logits"] = logits.numpy()
+    for i in range(2):
+        out["train_prop%d" % i] = props[i].numpy()
+        out["train_prop_labels%d" % i] = bls[i].get_field("labels").numpy()
+        out["train_prop_obj%d" % i] = bls[i].get_field("objectness").numpy()
+        out["train_gt%d" % i] = gts[i].numpy()
+        out["train_gt_labels%d" % i] = tgts[i].get_field("labels").numpy()
+    res = GridPostProcessor(1, 9, 14).forward({"unfused": logits.clone()}, bls, None, True, tgts)
+    for i, r in enumerate(res):
+        out["train_out_bbox%d" % i] = r.bbox.numpy()
+        out["train_out_labels%d" % i] = r.get_field("labels").numpy()
+        out["train_out_obj%d" % i] = r.get_field("objectness").numpy()
+    # ---- testing, stage 0, two images
+    props = [boxes(6), boxes(4)]
+    logits = torch.randn(10, 9, 28, 28, generator=g) * 2
+    bls = []
+    for p in props:
+        bl = BoxList(p.clone(), (1000, 800), mode="xyxy")
+        bl.add_field("scores", torch.rand(p.shape[0], generator=g))
+        bls.append(bl)
+    out["test0_logits"] = logits.numpy()
+    for i in range(2):
+        out["test0_prop%d" % i] = props[i].numpy()
+        out["test0_scores%d" % i] = bls[i].get_field("scores").numpy()
+    res = GridPostProcessor(0, 9, 14).forward({"unfused": logits.clone()}, bls, None, False)
+    for i, r in enumerate(res):
+        out["test0_out_bbox%d" % i] = r.bbox.numpy()
+        out["test0_out_scores%d" % i] = r.get_field("scores").numpy()
+    # ---- testing, last stage, one image, score *= iou probability
+    p = boxes(7)
+    logits = torch.randn(7, 9, 28, 28, generator=g) * 2
+    iou = torch.rand(7, 2, generator=g)
+    bl = BoxList(p.clone(), (1000, 800), mode="xyxy")
+    bl.add_field("scores", torch.rand(7, generator=g))
+    out.update(test2_logits=logits.numpy(), test2_prop=p.numpy(), test2_scores=bl.get_field("scores").numpy(),
+               test2_iou=iou.numpy())
+    r = GridPostProcessor(2, 9, 14).forward({"unfused": logits.clone()}, [bl], iou.clone(), False)[0]
+    out["test2_out_bbox"] = r.bbox.numpy()
+    out["test2_out_scores"] = r.get_field("scores").numpy()
+    np.savez_compressed(os.path.join(HERE, "grid_forward.npz"), **out)
+
+
 def main():
     build_ref.build(cuda=False)
     ref = build_ref.load("pet_ref_cpu")
     install_shims(ref)
-    only = [a for a in sys.argv[1:] if a in ("rpn", "detect", "grid_targets", "matcher")]
+    only = [a for a in sys.argv[1:] if a in ("rpn", "detect", "grid_targets", "matcher", "grid_forward")]
     if only:
         for a in only:
-            {"rpn": gen_rpn, "detect": gen_detect, "grid_targets": gen_grid_targets, "matcher": gen_matcher}[a]()
+            {"rpn": gen_rpn, "detect": gen_detect, "grid_targets": gen_grid_targets, "matcher": gen_matcher,
+             "grid_forward": gen_grid_forward}[a]()
             print(a + ".npz", os.path.getsize(os.path.join(HERE, a + ".npz")))
         return
     gen_rpn()
     gen_detect()
     gen_grid_targets()
     gen_matcher()
+    gen_grid_forward()
     feats, rois = gen_roi_align(ref)
     gen_pooler(feats, rois)
     gen_levels()

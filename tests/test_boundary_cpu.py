@@ -6,6 +6,7 @@ import inspect
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -145,3 +146,18 @@ def test_roi_table_and_boxlist_host_logic():
         ops.BoxList(torch.zeros(3, 5), (10, 10))
     sub_regions = ops.calc_sub_regions(9, 3, 56)                          # grid_rcnn/loss.py:244-273
     assert len(sub_regions) == 9 and all(0 <= v <= 28 for pt in sub_regions for v in pt[:2])
+
+
+def test_filter_not_gt_matches_the_reference(golden):
+    """GridPostProcessor._filter_boxes (inference.py:281-290) as a device-side mask: the rows the reference's own forward
+    kept (grid_forward.npz, training case) are exactly the rows the mask keeps."""
+    from cpm_r_cnn_b200.grid_decode import filter_not_gt
+    g = golden("grid_forward")
+    for i in range(2):
+        prop, gt = torch.from_numpy(g["train_prop%d" % i]), torch.from_numpy(g["train_gt%d" % i])
+        mask = filter_not_gt(prop, gt)
+        n_kept = g["train_out_bbox%d" % i].shape[0] - gt.shape[0]
+        assert int(mask.sum()) == n_kept
+        assert np.array_equal(g["train_out_labels%d" % i][:n_kept], g["train_prop_labels%d" % i][mask.numpy()])
+    assert filter_not_gt(torch.zeros(0, 4), torch.zeros(3, 4)).shape == (0,)
+    assert filter_not_gt(torch.ones(2, 4), torch.zeros(0, 4)).tolist() == [True, True]

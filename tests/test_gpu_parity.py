@@ -407,6 +407,41 @@ def test_grid_decode_golden(golden):
         assert torch.equal(out, out2)
 
 
+def test_grid_postprocessor_forward_golden(golden):
+    """GridPostProcessor.forward (inference.py:145-187) against the reference's own forward run on CPU: training (rows
+    equal to a ground truth dropped, the rest refined, ground truth appended) and testing (last stage: score * IoU prob)."""
+    g = golden("grid_forward")
+    size = (1000, 800)
+    props, tgts = [], []
+    for i in range(2):
+        bl = ops.BoxList(cuda(g["train_prop%d" % i]), size)
+        bl.add_field("labels", cuda(g["train_prop_labels%d" % i]))
+        bl.add_field("objectness", cuda(g["train_prop_obj%d" % i]))
+        tl = ops.BoxList(cuda(g["train_gt%d" % i]), size)
+        tl.add_field("labels", cuda(g["train_gt_labels%d" % i]))
+        props.append(bl)
+        tgts.append(tl)
+    res = ops.GridPostProcessor(1).forward({"unfused": cuda(g["train_logits"])}, props, None, True, tgts)
+    for i, r in enumerate(res):
+        np.testing.assert_allclose(r.bbox.cpu().numpy(), g["train_out_bbox%d" % i], rtol=1e-5, atol=1e-3)
+        assert np.array_equal(r.get_field("labels").cpu().numpy(), g["train_out_labels%d" % i])
+        assert np.array_equal(r.get_field("objectness").cpu().numpy(), g["train_out_obj%d" % i])
+    props = []
+    for i in range(2):
+        bl = ops.BoxList(cuda(g["test0_prop%d" % i]), size)
+        bl.add_field("scores", cuda(g["test0_scores%d" % i]))
+        props.append(bl)
+    res = ops.GridPostProcessor(0).forward({"unfused": cuda(g["test0_logits"])}, props, None, False)
+    for i, r in enumerate(res):
+        np.testing.assert_allclose(r.bbox.cpu().numpy(), g["test0_out_bbox%d" % i], rtol=1e-5, atol=1e-3)
+        assert np.array_equal(r.get_field("scores").cpu().numpy(), g["test0_out_scores%d" % i])
+    bl = ops.BoxList(cuda(g["test2_prop"]), size)
+    bl.add_field("scores", cuda(g["test2_scores"]))
+    r = ops.GridPostProcessor(2).forward({"unfused": cuda(g["test2_logits"])}, [bl], cuda(g["test2_iou"]), False)[0]
+    np.testing.assert_allclose(r.bbox.cpu().numpy(), g["test2_out_bbox"], rtol=1e-5, atol=1e-3)
+    assert np.array_equal(r.get_field("scores").cpu().numpy(), g["test2_out_scores"])
+
+
 def test_grid_decode_random_vs_oracle():
     gen = torch.Generator().manual_seed(31)
     R = 300
