@@ -31,3 +31,22 @@ for P, go_h in zip((7, 14), gouts_h):
         tb = timeit(lambda: pooler_backward(go, shapes, list(sy.FPN_SCALES), r, (P, P), 2, False, 0, mapper))
         tf = timeit(lambda: pooler_forward(feats, list(sy.FPN_SCALES), r, (P, P), 2, False, 0, mapper)) if r.shape[0] else 0.0
         print("P=%2d rois=%-4s K=%4d  bwd %.4f ms  fwd %.4f ms" % (P, sel_name, r.shape[0], tb, tf))
+# scan cost: the same RoIs moved far outside the image (same areas -> same levels and (level, image) lists, but no tile
+# is reached): every CTA scans its list, finds no candidate and stores zeros
+for P, go_h in zip((7, 14), gouts_h):
+    r = rois_h.clone()
+    r[:, 1:] += 1.0e5
+    r = r.to(dev)
+    go = go_h.to(dev)
+    tb = timeit(lambda: pooler_backward(go, shapes, list(sy.FPN_SCALES), r, (P, P), 2, False, 0, mapper))
+    print("P=%2d rois=outside K=%4d  bwd %.4f ms" % (P, r.shape[0], tb))
+# half / double the RoIs of the workload (same distribution)
+import torch as _t
+for P, go_h in zip((7, 14), gouts_h):
+    for frac in (0.25, 0.5):
+        n = int(rois_h.shape[0] * frac)
+        idx = _t.arange(0, rois_h.shape[0], int(1 / frac))
+        r = rois_h[idx].to(dev); go = go_h[idx].to(dev)
+        tb = timeit(lambda: pooler_backward(go, shapes, list(sy.FPN_SCALES), r, (P, P), 2, False, 0, mapper))
+        tf = timeit(lambda: pooler_forward(feats, list(sy.FPN_SCALES), r, (P, P), 2, False, 0, mapper))
+        print("P=%2d rois=%.2f K=%4d  bwd %.4f ms  fwd %.4f ms" % (P, frac, r.shape[0], tb, tf))
