@@ -165,18 +165,7 @@ struct TileGrid {
   int tiles_x[CPM_MAX_LEVELS], tiles_y[CPM_MAX_LEVELS];
   int first[CPM_MAX_LEVELS + 1];       // first tile id of the level in launch order (coarsest level first)
   int order[CPM_MAX_LEVELS];           // launch order -> level
-  // floor(2^32 / d) for the three divisors of the block-id decode (fast_div), so that no CTA spends its first
-  // few hundred cycles in integer divisions
-  unsigned m_tiles_x[CPM_MAX_LEVELS], m_per_img[CPM_MAX_LEVELS], m_chunks;
 };
-
-static unsigned div_magic(unsigned d) { return d <= 1 ? 0xffffffffu : (unsigned)((1ull << 32) / d); }
-// n / d for n < 2^32, d >= 1, m = div_magic(d): the estimate is never above and at most one below the quotient
-__device__ __forceinline__ int fast_div(int n, int d, unsigned m) {
-  int q = (int)__umulhi((unsigned)n, m);
-  if (n - q * d >= d) q++;
-  return q;
-}
 
 // workspace layout: int32 seg_count[L*B] ; int32 perm[L*B][K]
 __device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const float* __restrict__ rois, int K, const MapperView& mp,
@@ -347,17 +336,16 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
   __shared__ int wsum[8];
   const int C = pv.channels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int t = fast_div((int)blockIdx.x, chunks, tg.m_chunks);
-  const int c0 = ((int)blockIdx.x - t * chunks) * kChunk;
+  int t = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x % chunks) * kChunk;
   int oi = 0;
   while (oi + 1 < pv.num_levels && t >= tg.first[oi + 1]) oi++;
   const int l = tg.order[oi];
   t -= tg.first[oi];
   const int per_img = tg.tiles_x[l] * tg.tiles_y[l];
-  const int b = fast_div(t, per_img, tg.m_per_img[l]);
+  const int b = t / per_img;
   t -= b * per_img;
-  const int ty = fast_div(t, tg.tiles_x[l], tg.m_tiles_x[l]);
-  const int y0 = ty * TH, x0 = (t - ty * tg.tiles_x[l]) * TW;
+  const int y0 = (t / tg.tiles_x[l]) * TH, x0 = (t % tg.tiles_x[l]) * TW;
   const int H = pv.H[l], W = pv.W[l];
   const int cc = min(kChunk, C - c0);
   const bool active = 4 * lane < cc;
@@ -562,13 +550,8 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
   for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
 
   const int seg = l * pv.batch + b;
-  const int* plist = perm + (long)seg * K;
-  // the first round's list entries are fetched together with the list length (every list has K slots; what lies beyond
-  // the length is never used as an index): one memory round trip less at the head of every CTA
-  int first_me[2];
-#pragma unroll
-  for (int e = 0; e < 2; e++) first_me[e] = 2 * (int)threadIdx.x + e < K ? __ldg(plist + 2 * threadIdx.x + e) : -1;
   const int nseg = seg_count[seg];
+  const int* plist = perm + (long)seg * K;
 
   // staging constants of this thread
   //   transposing 4-byte copies: lane = (channel cl of a group of 4, bin j of a group of 8); the warp takes channel
@@ -586,7 +569,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
     for (int e = 0; e < 2; e++) {
       const int i = base + 2 * threadIdx.x + e;
       if (i < nseg) {
-        me[e] = base == 0 ? first_me[e] : plist[i];
+        me[e] = plist[i];
         const int4 bx = __ldg(box + me[e]);
         hit[e] = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
       }
@@ -934,10 +917,7 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
       tg.tiles_y[l] = (grad_feat->height[l] + TH - 1) / TH;
       tg.first[i] = (int)tiles;
       tiles += (long)B * tg.tiles_x[l] * tg.tiles_y[l];
-      tg.m_tiles_x[l] = div_magic((unsigned)tg.tiles_x[l]);
-      tg.m_per_img[l] = div_magic((unsigned)(tg.tiles_x[l] * tg.tiles_y[l]));
     }
-    tg.m_chunks = div_magic((unsigned)chunks);
     for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
     if (staged) {
