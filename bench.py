@@ -443,7 +443,13 @@ def run_ours(args):
                   for n in names}
         top = max(names, key=lambda n: op_ms[n])
         total_bytes = sum(ab[n] for n in names)
-        cpu_rate, cpu_dt, cpu_kind, cpu_sample = cpu_reference_rate(24) if world == 1 else (None, None, None, None)
+        # CPU baseline beside it: the full workload of the step (512 RoIs/img x 2 img), 4 passes (~10 s of CPU work)
+        cpu_rate = cpu_dt = cpu_kind = cpu_sample = None
+        if world == 1:
+            runs = [cpu_reference_rate(ROIS_PER_IMG) for _ in range(4)]
+            cpu_dt = sum(r[1] for r in runs)
+            cpu_rate = sum(r[0] * r[1] for r in runs) / cpu_dt          # units / total seconds
+            cpu_kind, cpu_sample = runs[0][2], runs[0][3] + ", 4 passes"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",

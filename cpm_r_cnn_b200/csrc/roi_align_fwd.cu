@@ -672,7 +672,7 @@ static int launch_rows(const PyramidView& pv, const float* rois, long K, int PH,
 int check_device_ptr(const void* p, const char* what);
 bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, int sampling_ratio, const void* d_out);
 int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
-                    const int* lv, float* out, int out_channels_last, cudaStream_t st);
+                    const int* lv, void* out, int out_channels_last, cudaStream_t st);
 
 int check_pyramid(const cpm_pyramid_t* p, const char* what) {
   CPM_CHECK_ARG(p != nullptr, "%s is NULL", what);
@@ -732,7 +732,10 @@ extern "C" int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d
   const int PP = pooled_h * pooled_w;
   const size_t smem_any = (size_t)(kChunk * (PP | 1) + 8) * sizeof(float);
   if (smem_any > 200 * 1024) nhwc_ok = false;
-  const bool cols_ok = nhwc_ok && interpolation == CPM_INTERP_BILINEAR &&
+  // a bf16 pyramid (bf16 pooled output) takes the same column-table kernel with 8-byte taps
+  const bool bf16_ok = feat->layout == CPM_LAYOUT_NHWC && feat->dtype == CPM_BF16 && interpolation == CPM_INTERP_BILINEAR &&
+                       (long)K * ((feat->channels + 63) / 64) < (1L << 31);
+  const bool cols_ok = (nhwc_ok || bf16_ok) && interpolation == CPM_INTERP_BILINEAR &&
                        fwd_cols_supported(feat, pooled_h, pooled_w, sampling_ratio, d_out);
   if (impl == CPM_FWD_COLS && !cols_ok) {
     set_error("CPM_FWD_COLS needs an NHWC fp32 pyramid, bilinear interpolation, a 7x7 or 14x14 pooler, sampling_ratio 1 or 2 "
@@ -740,7 +743,7 @@ extern "C" int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d
     return CPM_ERR_UNSUPPORTED;
   }
   if (cols_ok && (impl == CPM_FWD_AUTO || impl == CPM_FWD_COLS))
-    return launch_fwd_cols(pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, (float*)d_out,
+    return launch_fwd_cols(pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, d_out,
                            pooled_layout == CPM_POOLED_KHWC, st);
   if (pooled_layout == CPM_POOLED_KHWC) {
     set_error("a channels-last pooled output (CPM_POOLED_KHWC) is produced by the column-table kernel only: NHWC fp32 pyramid, "

@@ -18,6 +18,7 @@
 //           accumulators stay in registers, no dynamic register indexing, no per-sample control flow.
 //   out   = finished bins go to a shared-memory tile laid out exactly like the (K, C, PH, PW) output; the tile leaves
 //           with cp.async.bulk (one 25 KB bulk store per CTA at 7x7, one 784 B store per channel at 14x14).
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -81,6 +82,21 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t byte
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Storage type of the pyramid and of the pooled output: fp32, or bf16 (4 channels of a lane = one 8-byte tap, widened to
+// fp32 on arrival; all arithmetic is fp32, a finished bin is rounded to bf16 once).
+template <bool BF> struct Store { typedef float T; typedef ulonglong2 Tap; };
+template <> struct Store<true> { typedef __nv_bfloat16 T; typedef uint2 Tap; };
+
+// 4 channels of one lane as two packed fp32 pairs
+__device__ __forceinline__ void widen(const ulonglong2& t, u64& lo, u64& hi) {
+  lo = t.x;
+  hi = t.y;
+}
+__device__ __forceinline__ void widen(const uint2& t, u64& lo, u64& hi) {   // bf16 -> fp32: the bits move up by 16
+  lo = ((u64)(t.x & 0xffff0000u) << 32) | (u64)(t.x << 16);
+  hi = ((u64)(t.y & 0xffff0000u) << 32) | (u64)(t.y << 16);
+}
+
 template <int NG>
 struct Tables {
   TapS xt[32];                      // x sample taps (NS = 7*NG*G <= 28)
@@ -110,10 +126,29 @@ __device__ __forceinline__ void store_bin(float* __restrict__ tptr, int pw, int 
     tptr[3 * PP + pw] = b.y;
   }
 }
+template <int NG, bool OCL>
+__device__ __forceinline__ void store_bin(__nv_bfloat16* __restrict__ tptr, int pw, int ostride, u64 lo, u64 hi) {
+  constexpr int PP = 49 * NG * NG;
+  const float2 a = unpack2(lo), b = unpack2(hi);
+  if (OCL) {
+    const __nv_bfloat162 v0 = __floats2bfloat162_rn(a.x, a.y), v1 = __floats2bfloat162_rn(b.x, b.y);
+    uint2 v;
+    v.x = *reinterpret_cast<const unsigned*>(&v0);
+    v.y = *reinterpret_cast<const unsigned*>(&v1);
+    *reinterpret_cast<uint2*>(tptr + (size_t)pw * ostride) = v;
+  } else {
+    tptr[pw] = __float2bfloat16_rn(a.x);
+    tptr[PP + pw] = __float2bfloat16_rn(a.y);
+    tptr[2 * PP + pw] = __float2bfloat16_rn(b.x);
+    tptr[3 * PP + pw] = __float2bfloat16_rn(b.y);
+  }
+}
 
-template <int NG, int NR, int NW, bool OCL>
+template <int NG, int NR, int NW, bool OCL, bool BF>
 __device__ __forceinline__ void run_columns(const char* __restrict__ base, const unsigned (&rowoff)[4], const u64 (&wy)[4],
-                                            const Tables<NG>& tb, const int g, float* __restrict__ tptr, const int ostride) {
+                                            const Tables<NG>& tb, const int g, typename Store<BF>::T* __restrict__ tptr,
+                                            const int ostride) {
+  typedef typename Store<BF>::Tap Tap;
   constexpr int PP = 49 * NG * NG;
   u64 acc[kBins][2];
 #pragma unroll
@@ -125,14 +160,17 @@ __device__ __forceinline__ void run_columns(const char* __restrict__ base, const
 #pragma unroll 1
     for (; n > 0; --n, ++i) {
       const unsigned xo = (unsigned)tb.xoff[i];
-      ulonglong2 f[NR];
+      Tap f[NR];
 #pragma unroll
-      for (int k = 0; k < NR; k++) f[k] = __ldg(reinterpret_cast<const ulonglong2*>(base + (size_t)(rowoff[k] + xo)));
-      u64 vlo = mul2(wy[0], f[0].x), vhi = mul2(wy[0], f[0].y);
+      for (int k = 0; k < NR; k++) f[k] = __ldg(reinterpret_cast<const Tap*>(base + (size_t)(rowoff[k] + xo)));
+      u64 flo, fhi;
+      widen(f[0], flo, fhi);
+      u64 vlo = mul2(wy[0], flo), vhi = mul2(wy[0], fhi);
 #pragma unroll
       for (int k = 1; k < NR; k++) {
-        vlo = fma2(wy[k], f[k].x, vlo);
-        vhi = fma2(wy[k], f[k].y, vhi);
+        widen(f[k], flo, fhi);
+        vlo = fma2(wy[k], flo, vlo);
+        vhi = fma2(wy[k], fhi, vhi);
       }
       const u64* wp = reinterpret_cast<const u64*>(&tb.w[g][i][0]);
 #pragma unroll
@@ -161,14 +199,18 @@ struct RingCfg {
 __device__ __forceinline__ void cp_async16_ca(uint32_t sdst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8_ca(uint32_t sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NG, int NR, int NW, bool OCL>
+template <int NG, int NR, int NW, bool OCL, bool BF>
 __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, const unsigned (&rowoff)[4], const u64 (&wy)[4],
-                                                 const Tables<NG>& tb, const int g, float* __restrict__ tptr, const int ostride,
-                                                 ulonglong2* __restrict__ ring /* this lane's first slot */) {
+                                                 const Tables<NG>& tb, const int g, typename Store<BF>::T* __restrict__ tptr,
+                                                 const int ostride, ulonglong2* __restrict__ ring /* this lane's first slot */) {
+  typedef typename Store<BF>::Tap Tap;     // (a bf16 tap uses the first 8 bytes of the lane's 16-byte slot)
   constexpr int PP = 49 * NG * NG;
   constexpr int S = RingCfg<NG>::kStages, NRM = RingCfg<NG>::kRows;
   const uint32_t ring_s = smem_u32(ring);
@@ -184,7 +226,10 @@ __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, 
     if (col < iend) {
       const unsigned xo = (unsigned)tb.xoff[col];
 #pragma unroll
-      for (int k = 0; k < NR; k++) cp_async16_ca(ring_s + (uint32_t)((slot * NRM + k) * 512), base + (size_t)(rowoff[k] + xo));
+      for (int k = 0; k < NR; k++) {
+        if (BF) cp_async8_ca(ring_s + (uint32_t)((slot * NRM + k) * 512), base + (size_t)(rowoff[k] + xo));
+        else cp_async16_ca(ring_s + (uint32_t)((slot * NRM + k) * 512), base + (size_t)(rowoff[k] + xo));
+      }
     }
     cp_async_commit();
   };
@@ -198,14 +243,17 @@ __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, 
     for (; n > 0; --n, ++i) {
       issue(i + S - 1, pre);
       cp_async_wait<S - 1>();
-      ulonglong2 f[NR];
+      Tap f[NR];
 #pragma unroll
-      for (int k = 0; k < NR; k++) f[k] = ring[(slot * NRM + k) * 32];
-      u64 vlo = mul2(wy[0], f[0].x), vhi = mul2(wy[0], f[0].y);
+      for (int k = 0; k < NR; k++) f[k] = *reinterpret_cast<const Tap*>(ring + (slot * NRM + k) * 32);
+      u64 flo, fhi;
+      widen(f[0], flo, fhi);
+      u64 vlo = mul2(wy[0], flo), vhi = mul2(wy[0], fhi);
 #pragma unroll
       for (int k = 1; k < NR; k++) {
-        vlo = fma2(wy[k], f[k].x, vlo);
-        vhi = fma2(wy[k], f[k].y, vhi);
+        widen(f[k], flo, fhi);
+        vlo = fma2(wy[k], flo, vlo);
+        vhi = fma2(wy[k], fhi, vhi);
       }
       const u64* wp = reinterpret_cast<const u64*>(&tb.w[g][i][0]);
 #pragma unroll
@@ -224,36 +272,39 @@ __device__ __forceinline__ void run_columns_ring(const char* __restrict__ base, 
   cp_async_wait<0>();
 }
 
-template <int NG, int NR, bool OCL>
+template <int NG, int NR, bool OCL, bool BF>
 __device__ __forceinline__ void run_nw_ring(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
-                                            const int g, float* tptr, const int ostride, ulonglong2* ring) {
+                                            const int g, typename Store<BF>::T* tptr, const int ostride, ulonglong2* ring) {
   const int nw = tb.nw[g];
-  if (nw == 2) run_columns_ring<NG, NR, 2, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
-  else if (nw == 4) run_columns_ring<NG, NR, 4, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
-  else run_columns_ring<NG, NR, 7, OCL>(base, rowoff, wy, tb, g, tptr, ostride, ring);
+  if (nw == 2) run_columns_ring<NG, NR, 2, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride, ring);
+  else if (nw == 4) run_columns_ring<NG, NR, 4, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride, ring);
+  else run_columns_ring<NG, NR, 7, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride, ring);
 }
 
-template <int NG, int NR, bool OCL>
+template <int NG, int NR, bool OCL, bool BF>
 __device__ __forceinline__ void run_nw(const char* base, const unsigned (&rowoff)[4], const u64 (&wy)[4], const Tables<NG>& tb,
-                                       const int g, float* tptr, const int ostride) {
+                                       const int g, typename Store<BF>::T* tptr, const int ostride) {
   const int nw = tb.nw[g];
-  if (nw == 2) run_columns<NG, NR, 2, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
-  else if (nw == 4) run_columns<NG, NR, 4, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
-  else run_columns<NG, NR, 7, OCL>(base, rowoff, wy, tb, g, tptr, ostride);
+  if (nw == 2) run_columns<NG, NR, 2, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride);
+  else if (nw == 4) run_columns<NG, NR, 4, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride);
+  else run_columns<NG, NR, 7, OCL, BF>(base, rowoff, wy, tb, g, tptr, ostride);
 }
 
 // NG = 1: 7x7 pooler, CTA = 7 warps (one bin row each) x 128 channels.
 // NG = 2: 14x14 pooler, CTA = 14 warps (7 row pairs x 2 column groups) x 64 channels; half-warps own different bin rows.
-template <int NG, bool OCL>
+template <int NG, bool OCL, bool BF>
 __global__ void __launch_bounds__(224 * NG, NG == 1 ? 3 : 2)
 roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int aligned, MapperView mp,
-                   const int* __restrict__ roi_levels, float* __restrict__ out, int chunks, int cpc) {
+                   const int* __restrict__ roi_levels, typename Store<BF>::T* __restrict__ out, int chunks, int cpc) {
+  typedef typename Store<BF>::T T;
+  constexpr int ES = (int)sizeof(T);       // bytes per stored element
   constexpr int P = kBins * NG;            // pooled height == width
   constexpr int PP = P * P;
   constexpr int LPR = 32 / NG;             // lanes per bin row
   constexpr int CH = 4 * LPR;              // channels per CTA
-  constexpr int SK = NG == 1 ? 0 : 4;      // tile skew (floats) per 4 channels: keeps the 14x14 tile's rows 16-byte aligned
-  extern __shared__ __align__(16) float tile[];       // [CH][PP] (+ skew), the CTA's block of the output
+  constexpr int SK = NG == 1 ? 0 : 16 / ES;   // tile skew (16 bytes) per 4 channels: keeps the 14x14 tile's rows 16-byte aligned
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* const tile = reinterpret_cast<T*>(smem_raw);     // [CH][PP] (+ skew), the CTA's block of the output
   __shared__ Tables<NG> tb;
 
   const int C = pv.channels;
@@ -268,24 +319,24 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
   if (pv.num_levels > 1) l = roi_levels ? roi_levels[n] : fpn_level(roi[1], roi[2], roi[3], roi[4], mp);
   const RoiGeo<float> geo = roi_geometry<float>(roi, pv.scale[l < 0 || l >= pv.num_levels ? 0 : l], P, P, G, aligned != 0);
   const bool ok = l >= 0 && l < pv.num_levels && geo.b >= 0 && geo.b < pv.batch;
-  constexpr int kTileFloats = OCL ? 0 : CH * PP + SK * (CH / 4);      // a channels-last output needs no staging tile
-  constexpr int kTileBytes = (kTileFloats * 4 + 15) & ~15;
+  constexpr int kTileElems = OCL ? 0 : CH * PP + SK * (CH / 4);       // a channels-last output needs no staging tile
+  constexpr int kTileBytes = (kTileElems * ES + 15) & ~15;
   const bool store_issuer = NG == 1 ? threadIdx.x == 0 : threadIdx.x < CH / 4;  // threads that own bulk-store groups
   // tile -> out[n, c0 : c0 + CH, :, :], asynchronous: the next chunk's column loop runs while the tile drains
   auto store_tile = [&](int c0) {
     if (OCL) return;
     fence_async_smem();
     __syncthreads();
-    float* o = out + ((size_t)n * C + c0) * PP;
+    T* o = out + ((size_t)n * C + c0) * PP;
     if (NG == 1) {
       if (threadIdx.x == 0) {
-        bulk_s2g(o, tile, CH * PP * 4);
+        bulk_s2g(o, tile, CH * PP * ES);
         bulk_commit();
       }
     } else {
       if (threadIdx.x < CH / 4) {      // the skew sits between groups of 4 channels: one 3 136-byte store per group
         const int c4 = threadIdx.x;
-        bulk_s2g(o + (size_t)c4 * 4 * PP, tile + c4 * (4 * PP + SK), 4 * PP * 4);
+        bulk_s2g(o + (size_t)c4 * 4 * PP, tile + c4 * (4 * PP + SK), 4 * PP * ES);
         bulk_commit();
       }
     }
@@ -300,10 +351,13 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
       const int c0 = (grp * cpc + ci) * CH;
       tile_free(ci);
       if (OCL) {
-        for (int e = threadIdx.x; e < PP * (CH / 4); e += blockDim.x)
-          *reinterpret_cast<float4*>(out + ((size_t)n * PP + e / (CH / 4)) * C + c0 + 4 * (e % (CH / 4))) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = threadIdx.x; e < PP * (CH / 4); e += blockDim.x) {
+          T* z = out + ((size_t)n * PP + e / (CH / 4)) * C + c0 + 4 * (e % (CH / 4));
+          if (BF) *reinterpret_cast<uint2*>(z) = make_uint2(0u, 0u);
+          else *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       } else {
-        for (int e = threadIdx.x; e < kTileFloats; e += blockDim.x) tile[e] = 0.f;
+        for (int e = threadIdx.x; e < kTileBytes / 4; e += blockDim.x) reinterpret_cast<unsigned*>(smem_raw)[e] = 0u;
       }
       store_tile(c0);
     }
@@ -344,11 +398,11 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
       __syncwarp();
       if (newlo) {
         tb.xcol[ilo] = t.lo;
-        tb.xoff[ilo] = t.lo * C * 4;
+        tb.xoff[ilo] = t.lo * C * ES;
       }
       if (newhi) {
         tb.xcol[ihi] = t.hi;
-        tb.xoff[ihi] = t.hi * C * 4;
+        tb.xoff[ihi] = t.hi * C * ES;
       }
       if (valid) {
         const int bin = lane / G;
@@ -415,10 +469,10 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
       const bool newhi = lo >= 0 && hi > lo && (!has_prev || hi > hi_prev);
       const int chunk = grp;
       const int chunks = groups;       // the RoI's CTAs share the rows round-robin
-      const char* img = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C);
-      const unsigned bytes = (unsigned)(xmax - xmin + 1) * (unsigned)C * 4u;
-      if (xany && newlo && lo % chunks == chunk) bulk_prefetch_l2(img + ((size_t)lo * W + xmin) * C * 4, bytes);
-      if (xany && newhi && hi % chunks == chunk) bulk_prefetch_l2(img + ((size_t)hi * W + xmin) * C * 4, bytes);
+      const char* img = reinterpret_cast<const char*>(pv.ptr[l]) + (size_t)geo.b * H * W * C * ES;
+      const unsigned bytes = (unsigned)(xmax - xmin + 1) * (unsigned)C * (unsigned)ES;
+      if (xany && newlo && lo % chunks == chunk) bulk_prefetch_l2(img + ((size_t)lo * W + xmin) * C * ES, bytes);
+      if (xany && newhi && hi % chunks == chunk) bulk_prefetch_l2(img + ((size_t)hi * W + xmin) * C * ES, bytes);
     }
     // ---- this lane's bin row: distinct feature rows and their (count-normalised) weights ----
     const int g = NG == 1 ? 0 : warp / kBins;
@@ -460,7 +514,7 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int y = j < nrow ? ry[j] : (nrow > 0 ? ry[0] : 0);        // padding rows re-read a row already in L1, weight 0
-        rowoff[j] = (unsigned)y * (unsigned)(W * C * 4);
+        rowoff[j] = (unsigned)y * (unsigned)(W * C * ES);
         if (j >= nrow) wyf[j] = 0.f;
       }
     }
@@ -491,17 +545,17 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
     }
     __syncthreads();
     // ---- main loop, once per channel chunk ----
-    ulonglong2* ring = reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(tile) + kTileBytes + warp * RingCfg<NG>::kWarpBytes) + lane;
+    ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem_raw + kTileBytes + warp * RingCfg<NG>::kWarpBytes) + lane;
     for (int ci = 0; ci < cpc; ci++) {
       const int c0 = (grp * cpc + ci) * CH;
-      const char* base = reinterpret_cast<const char*>((const float*)pv.ptr[l] + (size_t)geo.b * H * W * C + c0 + 4 * lr);
-      float* tptr = OCL ? out + ((size_t)n * PP + ph * P + kBins * g) * C + c0 + 4 * lr
-                        : tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
+      const char* base = reinterpret_cast<const char*>(pv.ptr[l]) + ((size_t)geo.b * H * W * C + c0 + 4 * lr) * ES;
+      T* tptr = OCL ? out + ((size_t)n * PP + ph * P + kBins * g) * C + c0 + 4 * lr
+                    : tile + (4 * lr) * PP + SK * lr + ph * P + kBins * g;
       tile_free(ci);
-      if (nr == 2) run_nw_ring<NG, 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-      else if (nr == 3) run_nw_ring<NG, 3, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-      else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2, OCL>(base, rowoff, wy, tb, g, tptr, C, ring);
-      else run_nw<NG, 4, OCL>(base, rowoff, wy, tb, g, tptr, C);
+      if (nr == 2) run_nw_ring<NG, 2, OCL, BF>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else if (nr == 3) run_nw_ring<NG, 3, OCL, BF>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else if (RingCfg<NG>::kRows >= 4) run_nw_ring<NG, RingCfg<NG>::kRows >= 4 ? 4 : 2, OCL, BF>(base, rowoff, wy, tb, g, tptr, C, ring);
+      else run_nw<NG, 4, OCL, BF>(base, rowoff, wy, tb, g, tptr, C);
       store_tile(c0);
     }
   }
@@ -512,7 +566,8 @@ roi_align_fwd_cols(PyramidView pv, const float* __restrict__ rois, int G, int al
 
 // true when the kernel above can take the call (checked by cpm_roi_align_forward)
 bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, int sampling_ratio, const void* d_out) {
-  if (feat->layout != CPM_LAYOUT_NHWC || feat->dtype != CPM_F32) return false;
+  if (feat->layout != CPM_LAYOUT_NHWC || (feat->dtype != CPM_F32 && feat->dtype != CPM_BF16)) return false;
+  const double es = feat->dtype == CPM_BF16 ? 2.0 : 4.0;
   if (pooled_h != pooled_w || (pooled_h != 7 && pooled_h != 14)) return false;
   if (sampling_ratio != 1 && sampling_ratio != 2) return false;
   const int ch = pooled_h == 7 ? 128 : 64;
@@ -520,7 +575,7 @@ bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
   if (((uintptr_t)d_out & 15) != 0) return false;
   for (int l = 0; l < feat->num_levels; l++) {
     if (((uintptr_t)feat->d_level[l] & 15) != 0) return false;
-    if ((double)feat->height[l] * feat->width[l] * feat->channels * 4.0 >= 2147483648.0) return false;   // 32-bit row offsets
+    if ((double)feat->height[l] * feat->width[l] * feat->channels * es >= 2147483648.0) return false;   // 32-bit row offsets
   }
   return true;
 }
@@ -532,28 +587,38 @@ static int chunks_per_cta(int chunks, int want) {
   return want < 1 ? 1 : want;
 }
 
-int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
-                    const int* lv, float* out, int out_channels_last, cudaStream_t st) {
+template <bool BF>
+static int launch_fwd_cols_t(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
+                             const int* lv, void* out_, int out_channels_last, cudaStream_t st) {
+  typedef typename fwdc::Store<BF>::T T;
+  T* out = (T*)out_;
   const size_t ring1 = 7 * fwdc::RingCfg<1>::kWarpBytes, ring2 = 14 * fwdc::RingCfg<2>::kWarpBytes;
-  const size_t smem1 = (out_channels_last ? 0 : (size_t)128 * 49 * 4) + ring1;
-  const size_t smem2 = (out_channels_last ? 0 : (size_t)(64 * 196 + 4 * 16) * 4) + ring2;
+  const size_t smem1 = (out_channels_last ? 0 : (size_t)128 * 49 * sizeof(T)) + ring1;
+  const size_t smem2 = (out_channels_last ? 0 : ((size_t)64 * 196 * sizeof(T) + 16 * 16)) + ring2;
   if (P == 7) {
     const int chunks = pv.channels / 128;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
-    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<1, true> : fwdc::roi_align_fwd_cols<1, false>;
+    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<1, true, BF> : fwdc::roi_align_fwd_cols<1, false, BF>;
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     const int cpc = chunks_per_cta(chunks, 1);
     fn<<<(unsigned)(K * (chunks / cpc)), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   } else {
     const int chunks = pv.channels / 64;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
-    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<2, true> : fwdc::roi_align_fwd_cols<2, false>;
+    auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<2, true, BF> : fwdc::roi_align_fwd_cols<2, false, BF>;
     CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int cpc = chunks_per_cta(chunks, 2);
     fn<<<(unsigned)(K * (chunks / cpc)), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   }
   CPM_CHECK_LAUNCH();
   return CPM_OK;
+}
+
+// `out` has the pyramid's storage type (fp32 or bf16)
+int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
+                    const int* lv, void* out, int out_channels_last, cudaStream_t st) {
+  return pv.dtype == CPM_BF16 ? launch_fwd_cols_t<true>(pv, rois, K, P, G, aligned, mp, lv, out, out_channels_last, st)
+                              : launch_fwd_cols_t<false>(pv, rois, K, P, G, aligned, mp, lv, out, out_channels_last, st);
 }
 
 }  // namespace cpm

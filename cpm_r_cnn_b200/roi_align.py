@@ -86,7 +86,6 @@ def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, i
                            % x0.dtype)
     if bf16 and (interpolation != 0 or x0.shape[1] % 8 != 0):
         raise RuntimeError("cpm_ops: the bf16 path needs bilinear interpolation and C % 8 == 0")
-    channels_last = channels_last and not bf16
     ph, pw = output_size
     K, C = rois.shape[0], x0.shape[1]
     out = torch.empty((K, C, ph, pw), dtype=x0.dtype, device=x0.device,

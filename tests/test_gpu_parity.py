@@ -637,6 +637,28 @@ def test_roi_align_native_bf16(pooled, sr):
     assert all(x.grad is not None and x.grad.dtype == torch.bfloat16 and torch.isfinite(x.grad.float()).all() for x in xg)
 
 
+@pytest.mark.parametrize("P,C,sr", [(7, 128, 2), (14, 128, 2), (7, 256, 1), (14, 64, 1)])
+def test_roi_align_bf16_column_kernel(P, C, sr):
+    """The column-table kernel on a bf16 pyramid (8-byte taps widened to fp32, one rounding of the pooled value): same
+    bound as above against the fp32 kernel on the same bf16-rounded features, every RoI size regime, both pooled layouts
+    (bit-identical to each other)."""
+    B = 2
+    gen = torch.Generator().manual_seed(23)
+    xb = [f.to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last) for f in synthetic.pyramid(gen, B, C, 200, 336)]
+    xf = [f.float() for f in xb]
+    rois = torch.cat([synthetic.coco_like_rois(gen, 48, B, 200, 336), _size_sweep_rois(4, B),
+                      synthetic.adversarial_rois(200, 336, B)], 0).cuda()
+    m = _lib.make_mapper(2, 5)
+    ref = pooler_forward(xf, SCALES, rois, (P, P), sr, False, 0, m, impl=_lib.FWD_COLS).double().cpu().numpy()
+    out = pooler_forward(xb, SCALES, rois, (P, P), sr, False, 0, m, impl=_lib.FWD_COLS)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous()
+    got = out.double().cpu().numpy()
+    rms = float(np.sqrt(np.mean(ref ** 2)))
+    assert np.all(np.abs(got - ref) <= 2.0 ** -8 * np.abs(ref) + 2.0 ** -8 * 1e-2 * rms)
+    cl = pooler_forward(xb, SCALES, rois, (P, P), sr, False, 0, m, impl=_lib.FWD_COLS, channels_last=True)
+    assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl, out)
+
+
 def test_backward_many_rois_per_image_multi_round():
     """More RoIs on one (level, image) than one scan round of the tile kernel holds (512): the per-tile candidate scan
     runs in several rounds and the RoI order -- hence the bit pattern -- must not depend on the round boundaries."""
