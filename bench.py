@@ -325,6 +325,43 @@ def run_ours(args):
         cl_ms = {"error": repr(ex)[:200]}
     sync_all()
 
+    # ---- forward on a bf16 pyramid (bf16 pooled output, fp32 arithmetic): reported separately, own algorithmic bytes
+    #      (2 bytes per stored element); the tolerance of this path is stated in tests/test_gpu_parity.py ----
+    bf16_ms = {}
+    try:
+        if "bf16" in os.environ.get("CPM_BENCH_SKIP", ""):
+            raise RuntimeError("skipped")
+        feats16 = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
+        b_fns = [(lambda p=p: pooler_forward(feats16, scales, rois, p, SAMPLING, False, 0, mapper)) for p in POOLERS]
+        with torch.cuda.stream(side):
+            for fn in b_fns:
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        sync_all()
+        b_graphs, b_keep = [], []
+        for fn in b_fns:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                b_keep.append(fn())
+            b_graphs.append(g)
+        n_b = max(3, min(args.steps, 20))
+        acc = [0.0] * len(b_graphs)
+        for it in range(n_b + 2):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(len(b_graphs) + 1)]
+            for j, g in enumerate(b_graphs):
+                e[j].record()
+                g.replay()
+            e[len(b_graphs)].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                for j in range(len(b_graphs)):
+                    acc[j] += e[j].elapsed_time(e[j + 1])
+        bf16_ms = {"fwd%d" % p[0]: acc[j] / n_b for j, p in enumerate(POOLERS)}
+        del b_graphs, b_keep, feats16
+    except Exception as ex:
+        bf16_ms = {"error": repr(ex)[:200]}
+    sync_all()
+
     # ---- the red.global.add fallback of the backward (non-deterministic order), reported separately ----
     atomic_ms = {}
     try:
@@ -472,6 +509,10 @@ def run_ours(args):
                                       "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
                              "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]},
                              "backward_atomic_fallback_ms": atomic_ms,
+                             "fwd_bf16_storage": ({n: {"ms": bf16_ms[n], "bytes": (ab[n] - 20 * K) // 2 + 20 * K,
+                                                       "gbs": ((ab[n] - 20 * K) // 2 + 20 * K) / (bf16_ms[n] * 1e-3) / 1e9,
+                                                       "frac": ((ab[n] - 20 * K) // 2 + 20 * K) / (bf16_ms[n] * 1e-3) / 1e9 / peak}
+                                                   for n in bf16_ms} if "error" not in bf16_ms else bf16_ms),
                              "ops_channels_last_pooled": ({n: {"ms": cl_ms[n], "gbs": ab[n] / (cl_ms[n] * 1e-3) / 1e9,
                                                                "frac": ab[n] / (cl_ms[n] * 1e-3) / 1e9 / peak} for n in names}
                                                           if "error" not in cl_ms else cl_ms)},
