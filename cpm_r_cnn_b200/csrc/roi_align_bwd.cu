@@ -505,8 +505,12 @@ struct Smem {
   int wsum[8];
 };
 
+// WIDE: the L2 fetches 256 bytes around the word -- the rest of a 784-byte channel row of a 14x14 gradient is wanted by the
+// next few copies anyway (0.272 -> 0.268 ms); for the 196-byte rows of a 7x7 gradient it only costs (0.131 -> 0.133 ms)
+template <bool WIDE>
 __device__ __forceinline__ void cp_async4(uint32_t sdst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+  if (WIDE) asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t sdst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
@@ -698,10 +702,10 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
           const int pp = (pq * magic) >> 16, qq = pq - pp * nq;
           const float* s = gth + (pp * PW + qq);
           const uint32_t d = sth + pq * (SROW * 4);
-          cp_async4(d, s);
-          cp_async4(d + 128, s + 32 * PP);
-          cp_async4(d + 256, s + 64 * PP);
-          cp_async4(d + 384, s + 96 * PP);
+          cp_async4<(PC >= 12)>(d, s);
+          cp_async4<(PC >= 12)>(d + 128, s + 32 * PP);
+          cp_async4<(PC >= 12)>(d + 256, s + 64 * PP);
+          cp_async4<(PC >= 12)>(d + 384, s + 96 * PP);
         }
       } else {
         for (int pq = j; pq < nb; pq += 8) {
@@ -711,7 +715,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const int c = cth + 32 * k;
-            if (c < cc) cp_async4(d + c * 4, s + (long)c * PP);
+            if (c < cc) cp_async4<false>(d + c * 4, s + (long)c * PP);
           }
         }
       }
