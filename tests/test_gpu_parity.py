@@ -459,6 +459,35 @@ def test_grid_decode_random_vs_oracle():
     np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=1e-6, atol=1e-6)
 
 
+def test_grid_decode_streaming_kernel_matches_per_roi_kernel(monkeypatch):
+    """Large batches go through the persistent streaming kernel (bulk copies into shared memory, two RoIs ahead); it
+    must return exactly what the one-CTA-per-RoI kernel returns (same arithmetic on the same values), including
+    saturated / tied / NaN maps and an R that is not a multiple of the grid."""
+    gen = torch.Generator().manual_seed(37)
+    R = 2048 + 777
+    logits = torch.randn(R, 9, 28, 28, generator=gen) * 2
+    logits[5] = 30.0                       # saturated: every sigmoid is exactly 1.0 -> first index
+    logits[6, 3] = float("nan")            # an all-NaN map decodes as index 0
+    logits[7, :, 10, 10] = 9.5
+    logits[7, :, 20, 3] = 9.5              # exact tie -> the first index wins
+    boxes = synthetic.coco_like_boxes(gen, R)
+    sub = ops.calc_sub_regions(9, 3, 56)
+    lg, bx = logits.cuda(), boxes.cuda()
+    out_s, sc_s = ops.grid_decode(lg, bx, sub, 0.25, return_scores=True)          # R >= 2048: streaming kernel
+    outs, scs = [], []
+    for a in range(0, R, 1000):                                                   # chunks below the threshold: per-RoI kernel
+        o, c = ops.grid_decode(lg[a:a + 1000], bx[a:a + 1000], sub, 0.25, return_scores=True)
+        outs.append(o)
+        scs.append(c)
+    out_p, sc_p = torch.cat(outs), torch.cat(scs)
+    assert torch.equal(sc_s, sc_p)
+    assert torch.equal(torch.nan_to_num(out_s, nan=-1.0), torch.nan_to_num(out_p, nan=-1.0))
+    ref = oracle.grid_decode(logits[:64].numpy(), boxes[:64].numpy(), sub, 0.25)
+    ok = np.ones(64, bool)
+    ok[[5, 6, 7]] = False
+    np.testing.assert_allclose(out_s[:64].cpu().numpy()[ok], ref[ok], rtol=1e-5, atol=1e-3)
+
+
 def test_grid_decode_saturation_ties_and_nan():
     """The register fast path finds the arg-max on the logits and evaluates the sigmoid only near the maximum and in the
     band where fp32 sigmoids collide (>= 8, saturating to exactly 1.0 from ~17): the reference's rule -- largest sigmoid,
