@@ -43,8 +43,15 @@ __device__ __forceinline__ void point_argmax_regs(const float4* __restrict__ m4,
     mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
   }
   const float lmx = mx;                  // this lane's largest logit
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  {
+    // warp maximum with one redux.sync: floats ordered as signed integers after flipping the magnitude bits of negatives
+    // (lmx is never NaN: fmaxf dropped them)
+    int key = __float_as_int(lmx);
+    key ^= (key >> 31) & 0x7fffffff;
+    key = __reduce_max_sync(0xffffffffu, key);
+    key ^= (key >> 31) & 0x7fffffff;
+    mx = __int_as_float(key);
+  }
   const float t = fminf(mx - 1e-3f, 8.0f);
   // (NaN logits fail `>= t` and fmaxf ignores them, so they never win -- as in the reference's `>` comparison; an
   //  all-NaN map leaves bi unset and decodes as index 0)
@@ -82,7 +89,8 @@ __device__ __forceinline__ void point_argmax_regs(const float4* __restrict__ m4,
 
 __global__ void __launch_bounds__(288, 4) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                                            int P, int gs, int h, int w, SubXY sub, float ratio,
-                                                           float* __restrict__ out_boxes, float* __restrict__ out_scores) {
+                                                           float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                           unsigned wmagic) {
   __shared__ float sc[kMaxPoints], ax[kMaxPoints], ay[kMaxPoints];
   const long r = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -122,7 +130,8 @@ __global__ void __launch_bounds__(288, 4) grid_decode_kernel(const float* __rest
     }
     if (lane == 0) {
       if (bi == 0x7fffffff) bi = 0;   // all-NaN map
-      const int xs = bi % w + sub.v[2 * p], ys = bi / w + sub.v[2 * p + 1];
+      const int row = wmagic ? (int)(((unsigned)bi * wmagic) >> 16) : bi / w;
+      const int xs = bi - row * w + sub.v[2 * p], ys = row + sub.v[2 * p + 1];
       sc[p] = bs;
       ax[p] = ((float)xs + 0.5f) / (float)(2 * w) * (1.f + ratio) * width + x1;      // inference.py:246
       ay[p] = ((float)ys + 0.5f) / (float)(2 * h) * (1.f + ratio) * height + y1;     // inference.py:247
@@ -177,7 +186,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __global__ void __launch_bounds__(288, 3) grid_decode_stream_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                                                   long R, int P, int gs, int h, int w, SubXY sub, float ratio,
                                                                   float* __restrict__ out_boxes, float* __restrict__ out_scores,
-                                                                  uint32_t roi_bytes, uint32_t stage_bytes) {
+                                                                  uint32_t roi_bytes, uint32_t stage_bytes, unsigned wmagic) {
   extern __shared__ __align__(128) unsigned char stage_mem[];
   __shared__ uint64_t full[kStreamStages];
   __shared__ float sc[kStreamStages][kMaxPoints], ax[kStreamStages][kMaxPoints], ay[kStreamStages][kMaxPoints];
@@ -218,7 +227,8 @@ __global__ void __launch_bounds__(288, 3) grid_decode_stream_kernel(const float*
       }
       if (lane == 0) {
         if (bi == 0x7fffffff) bi = 0;   // all-NaN map
-        const int xs = bi % w + sub.v[2 * p], ys = bi / w + sub.v[2 * p + 1];
+        const int row = wmagic ? (int)(((unsigned)bi * wmagic) >> 16) : bi / w;
+      const int xs = bi - row * w + sub.v[2 * p], ys = row + sub.v[2 * p + 1];
         sc[s][p] = bs;
         ax[s][p] = ((float)xs + 0.5f) / (float)(2 * w) * (1.f + ratio) * width + x1;      // inference.py:246
         ay[s][p] = ((float)ys + 0.5f) / (float)(2 * h) * (1.f + ratio) * height + y1;     // inference.py:247
@@ -278,6 +288,11 @@ extern "C" int cpm_grid_decode(const float* d_logits, const float* d_boxes, int6
   for (int i = 2 * P; i < 2 * kMaxPoints; i++) sub.v[i] = 0;
   int warps = P < 8 ? P : 8;
   if (P == 9) warps = 9;
+  // i / w == (i * wmagic) >> 16 for every index of the map (checked here; 0 = divide in the kernel)
+  unsigned wmagic = (65536u + (unsigned)w - 1) / (unsigned)w;
+  if ((long)h * w > 4096) wmagic = 0;
+  for (int i = 0; wmagic && i < h * w; i++)
+    if ((((unsigned)i * wmagic) >> 16) != (unsigned)(i / w)) wmagic = 0;
   // large batches stream the RoIs through persistent CTAs (bulk copies, two RoIs ahead); small ones are latency-bound
   // anyway and keep one CTA per RoI
   const int hw = h * w;
@@ -290,12 +305,12 @@ extern "C" int cpm_grid_decode(const float* d_logits, const float* d_boxes, int6
     const long ctas = R < 148L * 3 ? R : 148L * 3;
     grid_decode_stream_kernel<<<(unsigned)ctas, 32 * warps, smem, (cudaStream_t)stream>>>(
         d_logits, d_boxes, R, P, gs, h, w, sub, mapping_ratio, d_out_boxes, d_out_scores, (uint32_t)roi_bytes,
-        (uint32_t)stage_bytes);
+        (uint32_t)stage_bytes, wmagic);
     CPM_CHECK_LAUNCH();
     return CPM_OK;
   }
   grid_decode_kernel<<<(unsigned)R, 32 * warps, 0, (cudaStream_t)stream>>>(d_logits, d_boxes, P, gs, h, w, sub,
-                                                                          mapping_ratio, d_out_boxes, d_out_scores);
+                                                                          mapping_ratio, d_out_boxes, d_out_scores, wmagic);
   CPM_CHECK_LAUNCH();
   return CPM_OK;
 }
