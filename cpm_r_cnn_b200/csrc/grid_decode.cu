@@ -32,6 +32,16 @@ __device__ __forceinline__ void argmax_merge(float& bs, int& bi, float s, int i)
 
 // Register-resident arg-max of one heat-map of n4 <= 32 * kRegVec float4 (see the comment at the call site): pass 1 finds the
 // largest logit, pass 2 evaluates the sigmoid only where fp32 sigmoids can tie.  SMEM: the map is in shared memory.
+__device__ __forceinline__ void warp_argmax(float& bs, int& bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    argmax_merge(bs, bi, s2, i2);
+  }
+}
+
+// On return (bs, bi) is the same on every lane of the warp.
 template <bool SMEM>
 __device__ __forceinline__ void point_argmax_regs(const float4* __restrict__ m4, int n4, int lane, float& bs, int& bi) {
   float4 v[kRegVec];
@@ -85,6 +95,7 @@ __device__ __forceinline__ void point_argmax_regs(const float4* __restrict__ m4,
     if (v[k].z >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].z), i + 2);
     if (v[k].w >= t) argmax_merge(bs, bi, sigmoidf_ref(v[k].w), i + 3);
   }
+  warp_argmax(bs, bi);
 }
 
 __global__ void __launch_bounds__(288, 4) grid_decode_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
@@ -122,12 +133,7 @@ __global__ void __launch_bounds__(288, 4) grid_decode_kernel(const float* __rest
     } else {
       for (int i = lane; i < hw; i += 32) argmax_merge(bs, bi, sigmoidf_ref(__ldg(m + i)), i);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-      argmax_merge(bs, bi, s2, i2);
-    }
+    if (!((hw & 3) == 0 && hw <= 4 * 32 * kRegVec)) warp_argmax(bs, bi);   // (the register path returns warp-uniform values)
     if (lane == 0) {
       if (bi == 0x7fffffff) bi = 0;   // all-NaN map
       const int row = wmagic ? (int)(((unsigned)bi * wmagic) >> 16) : bi / w;
@@ -219,12 +225,6 @@ __global__ void __launch_bounds__(288, 3) grid_decode_stream_kernel(const float*
       float bs = -1.f;
       int bi = 0x7fffffff;
       point_argmax_regs<true>(reinterpret_cast<const float4*>(maps + (size_t)p * hw), hw >> 2, lane, bs, bi);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
-        argmax_merge(bs, bi, s2, i2);
-      }
       if (lane == 0) {
         if (bi == 0x7fffffff) bi = 0;   // all-NaN map
         const int row = wmagic ? (int)(((unsigned)bi * wmagic) >> 16) : bi / w;
