@@ -83,8 +83,8 @@ if args.nms:
     b, s, seg, lab, img = sy.detection_candidates(gen, 16, 1000, 80, -1.0)
     for i in range(2):
         ops.batched_nms(b.to(dev), s.to(dev), seg.to(dev), 1280, 0.3, sync=False)
-    logits = torch.randn(2000, 9, 28, 28, generator=gen).to(dev)
-    boxes = sy.coco_like_boxes(gen, 2000).to(dev)
+    logits = torch.randn(16000, 9, 28, 28, generator=gen).to(dev)     # the bench's decode size (streaming kernel)
+    boxes = sy.coco_like_boxes(gen, 16000).to(dev)
     sub = ops.calc_sub_regions(9, 3, 56)
     for i in range(2):
         ops.grid_decode(logits, boxes, sub, 0.5)
