@@ -161,3 +161,22 @@ def test_filter_not_gt_matches_the_reference(golden):
         assert np.array_equal(g["train_out_labels%d" % i][:n_kept], g["train_prop_labels%d" % i][mask.numpy()])
     assert filter_not_gt(torch.zeros(0, 4), torch.zeros(3, 4)).shape == (0,)
     assert filter_not_gt(torch.ones(2, 4), torch.zeros(0, 4)).tolist() == [True, True]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU RoIAlign on the host cores; no GPU needed): one JSON line with
+    the keys the driver reads, `impl: reference`, a cpu_baseline describing the run and an e2e object repeating the value."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "roi_align_fwd_bwd_rois_per_sec" and d["unit"] == "RoIs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
