@@ -467,11 +467,7 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
 //     combine first, in a fixed order: deterministic, no atomics.
 namespace bst {
 
-// Bins per staging buffer.  48 rather than 56 for a (K,C,PH,PW) gradient: at 62 KB per CTA three CTAs fit the 196 KB
-// shared-memory carve-out, which leaves the SM a 60 KB L1 instead of 28 KB -- the 4-byte transposing copies hit it (the
-// neighbouring bins of a channel share 32-byte sectors): 14x14 0.266 -> 0.223 ms, 7x7 0.131 -> 0.127 ms.  A channels-last
-// gradient is staged with 16-byte copies that do not care, and prefers fewer, larger items (56).
-constexpr int kBinsDeep = 56, kBinsL1 = 48;
+constexpr int NBUF = 56;               // bins per staging buffer (4 bin rows of a 14-wide pooler)
 constexpr int SROW = kChunk + 4;       // floats per staged bin (528 B: rows stay 16-byte aligned, 4-byte stores conflict-free)
 constexpr int kRound = 2 * kTileThreads;   // RoIs of the (level, image) list scanned per round
 constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the tables hold (the path needs P * G <= 32)
@@ -481,16 +477,14 @@ constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the
 struct ItemTables {
   unsigned char npg[33];
   unsigned int magic[33];
-  constexpr ItemTables() : npg(), magic() {}
-  constexpr ItemTables(int nb) : npg(), magic() {
+  constexpr ItemTables() : npg(), magic() {
     for (int n = 1; n <= 32; n++) {
-      npg[n] = (unsigned char)(nb / n < MAXP ? nb / n : MAXP);
+      npg[n] = (unsigned char)(NBUF / n < MAXP ? NBUF / n : MAXP);
       magic[n] = (65536u + n - 1) / n;
     }
   }
 };
-__constant__ ItemTables kItemTablesDeep = ItemTables(kBinsDeep);
-__constant__ ItemTables kItemTablesL1 = ItemTables(kBinsL1);
+__constant__ ItemTables kItemTables = ItemTables();
 
 struct __align__(16) Item {
   long long gofs;                      // float offset of the sub-block's first element inside grad_out
@@ -500,7 +494,6 @@ struct __align__(16) Item {
   int pad[2];
 };
 
-template <int NBUF>
 struct Smem {
   float S[2][NBUF * SROW];
   float2 WX[2][MAXQ][TW];              // weights duplicated for FFMA2
@@ -534,9 +527,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
                  const int4* __restrict__ box, int K, int PH_, int PW_, int G_, const int* __restrict__ seg_count,
                  const int* __restrict__ perm, int chunks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NBUF = (GO_CL && PC != 7) ? kBinsDeep : kBinsL1;
-  Smem<NBUF>& sm = *reinterpret_cast<Smem<NBUF>*>(smem_raw);
-  const ItemTables& kItemTables = NBUF == kBinsDeep ? kItemTablesDeep : kItemTablesL1;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int PH = PC ? PC : PH_, PW = PC ? PC : PW_, G = GC ? GC : G_;
   const int C = pv.channels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -794,12 +785,8 @@ typedef void (*StagedFn)(PyramidView, TileGrid, const float*, const TapS*, const
                          const int*, int);
 
 template <bool GO_CL>
-static StagedFn pick_staged(int PH, int PW, int G, size_t* smem) {
-  *smem = GO_CL ? sizeof(Smem<kBinsDeep>) : sizeof(Smem<kBinsL1>);
-  if (PH == 7 && PW == 7 && G == 2) {
-    *smem = sizeof(Smem<kBinsL1>);
-    return bwd_tiles_staged<GO_CL, 7, 2>;
-  }
+static StagedFn pick_staged(int PH, int PW, int G) {
+  if (PH == 7 && PW == 7 && G == 2) return bwd_tiles_staged<GO_CL, 7, 2>;
   if (PH == 14 && PW == 14 && G == 2) return bwd_tiles_staged<GO_CL, 14, 2>;
   return bwd_tiles_staged<GO_CL, 0, 0>;
 }
@@ -938,12 +925,10 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
     if (staged) {
-      size_t smem = 0;
-      const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC
-                                   ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio, &smem)
-                                   : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio, &smem);
-      CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      fn<<<(unsigned)(tiles * chunks), kTileThreads, smem, st>>>(
+      const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio)
+                                                                : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
+      CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
+      fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
           pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
     } else {
       bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, goT, taps, box, Kp, pooled_h, pooled_w,
