@@ -467,7 +467,12 @@ __global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGr
 //     combine first, in a fixed order: deterministic, no atomics.
 namespace bst {
 
-constexpr int NBUF = 56;               // bins per staging buffer (4 bin rows of a 14-wide pooler)
+// Bins per staging buffer.  48 rather than 56: at 62 KB per CTA three CTAs fit the 196 KB shared-memory carve-out, which
+// leaves the SM a 60 KB L1 instead of 28 KB -- the 4-byte transposing copies of a (K,C,PH,PW) gradient hit it (neighbouring
+// bins of a channel share 32-byte sectors): 14x14 0.266 -> 0.223 ms, 7x7 0.131 -> 0.127 ms.  (A channels-last 14x14
+// gradient, staged with 16-byte copies, would rather have 56 -- 0.190 vs 0.195 ms -- but both layouts keep the same item
+// boundaries, so that their results stay bit-identical.)
+constexpr int NBUF = 48;
 constexpr int SROW = kChunk + 4;       // floats per staged bin (528 B: rows stay 16-byte aligned, 4-byte stores conflict-free)
 constexpr int kRound = 2 * kTileThreads;   // RoIs of the (level, image) list scanned per round
 constexpr int MAXQ = 32, MAXP = 16;    // bin columns / bin rows of one item the tables hold (the path needs P * G <= 32)
