@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each op's main kernel, from the committed `ncu --set full`
 # capture of this same workload (profiles/ncu_r01_summary.txt); not re-measured by bench.py (a run under ncu is never timed)
-NCU_DRAM_BYTES = {"fwd7": 157.0e6, "fwd14": 316.9e6, "bwd7": 179.9e6, "bwd14": 361.7e6}
+NCU_DRAM_BYTES = {"fwd7": 157.1e6, "fwd14": 316.0e6, "bwd7": 177.5e6, "bwd14": 361.2e6}
 NCU_DRAM_SOURCE = "profiles/ncu_r01_summary.txt (ncu --set full, one capture per kernel)"
 
 METRIC = "roi_align_fwd_bwd_rois_per_sec"
