@@ -51,6 +51,8 @@ _SIGNATURES = {
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "cpm_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "cpm_roi_align_backward_workspace_bytes_pyr": (ctypes.c_size_t, [ctypes.POINTER(Pyramid), ctypes.c_int64, ctypes.c_int,
+                                                                     ctypes.c_int, ctypes.c_int]),
     "cpm_roi_align_backward": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(LevelMapperC), ctypes.c_void_p, ctypes.c_int,

@@ -16,8 +16,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcpm_ops.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_bwd.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "matcher.cu", "layout.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "cpm_ops.h")]
+SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_bwd.cu", "roi_align_bwd_tma.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "matcher.cu", "layout.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "roi_align_bwd.cuh"), os.path.join(INCLUDE, "cpm_ops.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: no implicit contraction -- every fused multiply-add in the kernels is an explicit fmaf(), which is what

@@ -17,7 +17,10 @@
 //      Every pixel of every level is written exactly once (zeros where no RoI reaches), so no memset pass exists.
 // CPM_BWD_ATOMIC: zero-fill + scatter; NHWC fp32 uses red.global.add.v4.f32 (one 16-byte reduction per lane per tap),
 //   anything else (NCHW, fp64, nearest, adaptive grid) the reference-shaped scalar atomicAdd kernel.
-#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "roi_align_bwd.cuh"
 
 namespace cpm {
 
@@ -161,12 +164,6 @@ constexpr int TH = 8, TW = 8;          // tile: 8 rows (one per warp) x 8 column
 constexpr int kTileThreads = 256;
 constexpr int kMaxP = 32;              // pooled size limit of this path (bin ranges are 32-bit ballots)
 
-struct TileGrid {
-  int tiles_x[CPM_MAX_LEVELS], tiles_y[CPM_MAX_LEVELS];
-  int first[CPM_MAX_LEVELS + 1];       // first tile id of the level in launch order (coarsest level first)
-  int order[CPM_MAX_LEVELS];           // launch order -> level
-};
-
 // workspace layout: int32 seg_count[L*B] ; int32 perm[L*B][K]
 __device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const float* __restrict__ rois, int K, const MapperView& mp,
                                                const int* __restrict__ roi_levels, int* __restrict__ seg_count,
@@ -213,30 +210,12 @@ __device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const floa
   }
 }
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-  u64 d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-  return d;
-}
-
-struct __align__(16) TapS {
-  int lo, hi;       // lo < 0: sample out of range
-  float wlo, whi;   // (1 - l), l   (bilinear_interpolate_gradient, ROIAlign_cuda.cu:155-160, per axis)
-};
-
 // One CTA per RoI: the RoI's sample taps along both axes (PH*G + PW*G entries) and the pixel box they reach.
 // taps layout: [K][(PH + PW) * G]  (y taps first); box: [K] int4 {ylo, yhi, xlo, xhi}, ylo > yhi when nothing is reached.
 __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const float* __restrict__ rois, int PH, int PW, int G,
                                                int aligned, const MapperView& mp, const int* __restrict__ roi_levels,
                                                TapS* __restrict__ taps, int4* __restrict__ box, const int r, const int tid,
-                                               const int nthr) {
+                                               const int nthr, int* __restrict__ rowclip, const int NB) {
   const float* roi = rois + 5 * (long)r;
   const int l = roi_level_b(roi, pv, mp, roi_levels, r);
   const int nt = (PH + PW) * G;
@@ -248,6 +227,9 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
   }
   const int H = pv.H[l], W = pv.W[l];
   const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
+  TapS mine;
+  mine.lo = mine.hi = -1;
+  mine.wlo = mine.whi = 0.f;
   for (int e = tid; e < nt; e += nthr) {
     const bool isy = e < PH * G;
     const int k = isy ? e : e - PH * G;
@@ -261,6 +243,23 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
     o.wlo = t.wlo;
     o.whi = t.whi;
     out[e] = o;
+    if (e == tid) mine = o;
+  }
+  if (rowclip != nullptr && tid < 32) {
+    // (TMA tile kernel) per band of 8 pixel rows: first | last << 8 bin row with a sample tap inside the band.  The y taps
+    // of the RoI sit on lanes [0, PH * G) of the group's first warp (PH * G <= 32 on this path); they are monotone.
+    const bool v = tid < PH * G && mine.lo >= 0;
+    const unsigned valid = __ballot_sync(0xffffffffu, v);
+    for (int b = tid; b < NB; b += 32) rowclip[(long)r * NB + b] = 1;      // first 1 > last 0: no bin row in the band
+    __syncwarp();
+    if (valid) {
+      const int ylo = __shfl_sync(0xffffffffu, mine.lo, __ffs(valid) - 1);
+      const int yhi = __shfl_sync(0xffffffffu, mine.hi, 31 - __clz(valid));
+      for (int b = ylo >> 3; b <= (yhi >> 3) && b < NB; b++) {
+        const unsigned m = __ballot_sync(0xffffffffu, v && mine.hi >= 8 * b && mine.lo < 8 * b + 8);
+        if (tid == 0 && m) rowclip[(long)r * NB + b] = ((__ffs(m) - 1) / G) | (((31 - __clz(m)) / G) << 8);
+      }
+    }
   }
   if (tid == 0) {
     // sample coordinates are monotone along an axis, so the first / last sample bound the reached pixels
@@ -280,176 +279,16 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
 __global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* __restrict__ rois, int K, int PH, int PW, int G,
                                                     int aligned, MapperView mp, const int* __restrict__ roi_levels,
                                                     int* __restrict__ seg_count, int* __restrict__ perm,
-                                                    TapS* __restrict__ taps, int4* __restrict__ box) {
+                                                    TapS* __restrict__ taps, int4* __restrict__ box, int* __restrict__ rowclip,
+                                                    int NB) {
   const int nseg = pv.num_levels * pv.batch;
   if ((int)blockIdx.x < nseg) {
     bin_rois_block(pv, rois, K, mp, roi_levels, seg_count, perm, blockIdx.x);
   } else {
     const int r = 4 * ((int)blockIdx.x - nseg) + (threadIdx.x >> 6);
-    if (r < K) roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, 64);
+    if (r < K) roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, 64, rowclip, NB);
   }
 }
-
-__device__ __forceinline__ TapS ld_tap(const TapS* p) {
-  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
-  TapS t;
-  t.lo = v.x;
-  t.hi = v.y;
-  t.wlo = __int_as_float(v.z);
-  t.whi = __int_as_float(v.w);
-  return t;
-}
-
-__device__ __forceinline__ float tap_weight(const TapS& t, int pix) {
-  return (t.lo == pix ? t.wlo : 0.f) + (t.hi == pix ? t.whi : 0.f);
-}
-
-// (K, C, PP) -> (K, PP, C): the pooled gradient in channel-vector order, so that one bin of one RoI is one coalesced row
-template <typename T>
-__global__ void __launch_bounds__(256) transpose_go(const T* __restrict__ in, T* __restrict__ out, int R, int S) {
-  __shared__ T tile[32][33];
-  const long img = blockIdx.z;
-  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const T* src = in + img * (long)R * S;
-  T* dst = out + img * (long)R * S;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = r0 + ty + 8 * k, c = s0 + tx;
-    if (r < R && c < S) tile[ty + 8 * k][tx] = src[(long)r * S + c];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int c = s0 + ty + 8 * k, r = r0 + tx;
-    if (r < R && c < S) dst[(long)c * R + r] = tile[tx][ty + 8 * k];
-  }
-}
-
-// Tile-owner gather.  goT is (K, PH*PW, C).  After the candidate list of a 256-RoI round is built (two block barriers),
-// every warp walks the list on its own: no barrier, no shared-memory staging inside the RoI loop.
-__global__ void __launch_bounds__(kTileThreads) bwd_tiles(PyramidView pv, TileGrid tg, const float* __restrict__ goT,
-                                                           const TapS* __restrict__ taps, const int4* __restrict__ box, int K,
-                                                           int PH, int PW, int G, const int* __restrict__ seg_count,
-                                                           const int* __restrict__ perm, int chunks) {
-  __shared__ int cand[kTileThreads];
-  __shared__ int wsum[8];
-  const int C = pv.channels;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int t = blockIdx.x / chunks;
-  const int c0 = (blockIdx.x % chunks) * kChunk;
-  int oi = 0;
-  while (oi + 1 < pv.num_levels && t >= tg.first[oi + 1]) oi++;
-  const int l = tg.order[oi];
-  t -= tg.first[oi];
-  const int per_img = tg.tiles_x[l] * tg.tiles_y[l];
-  const int b = t / per_img;
-  t -= b * per_img;
-  const int y0 = (t / tg.tiles_x[l]) * TH, x0 = (t % tg.tiles_x[l]) * TW;
-  const int H = pv.H[l], W = pv.W[l];
-  const int cc = min(kChunk, C - c0);
-  const bool active = 4 * lane < cc;
-  const int PP = PH * PW;
-  const int nt = (PH + PW) * G;
-  const float invG = 1.0f / (float)G;
-  const int y = y0 + warp;
-
-  u64 acc[TW][2];
-#pragma unroll
-  for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
-
-  const int seg = l * pv.batch + b;
-  const int nseg = seg_count[seg];
-  const int* plist = perm + (long)seg * K;
-
-  for (int base = 0; base < nseg; base += kTileThreads) {
-    bool hit = false;
-    int me = -1;
-    if (base + threadIdx.x < nseg) {
-      me = plist[base + threadIdx.x];
-      const int4 bx = __ldg(box + me);
-      hit = bx.x <= bx.y && bx.x < y0 + TH && bx.y >= y0 && bx.z < x0 + TW && bx.w >= x0;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) wsum[warp] = __popc(bal);
-    __syncthreads();
-    int pos = __popc(bal & ((1u << lane) - 1)), ncand = 0;
-    for (int w = 0; w < 8; w++) {
-      if (w < warp) pos += wsum[w];
-      ncand += wsum[w];
-    }
-    if (hit) cand[pos] = me;
-    __syncthreads();
-
-    if (y < H) {
-      for (int ci = 0; ci < ncand; ci++) {
-        const int r = cand[ci];
-        const int4 bx = __ldg(box + r);
-        if (y < bx.x || y > bx.y) continue;             // this tile row is outside the RoI's reach (warp-uniform)
-        const TapS* tp = taps + (long)r * nt;
-        // lane p: weight of bin row p on pixel row y ; lane q: weights of bin column q on the 8 pixel columns
-        float wy = 0.f;
-        if (lane < PH)
-          for (int i = 0; i < G; i++) wy += tap_weight(ld_tap(tp + lane * G + i), y);
-        wy *= invG;
-        const unsigned pmask = __ballot_sync(0xffffffffu, wy != 0.f);
-        if (pmask == 0u) continue;
-        float wx[TW];
-#pragma unroll
-        for (int x = 0; x < TW; x++) wx[x] = 0.f;
-        if (lane < PW)
-          for (int i = 0; i < G; i++) {
-            const TapS tq = ld_tap(tp + PH * G + lane * G + i);
-#pragma unroll
-            for (int x = 0; x < TW; x++) wx[x] += tap_weight(tq, x0 + x);
-          }
-        unsigned qm[TW], qall = 0u;
-#pragma unroll
-        for (int x = 0; x < TW; x++) {
-          wx[x] *= invG;
-          qm[x] = __ballot_sync(0xffffffffu, wx[x] != 0.f);
-          qall |= qm[x];
-        }
-        if (qall == 0u) continue;
-        const float* gr = goT + (long)r * PP * C + c0 + 4 * lane;
-        unsigned pm = pmask;
-        while (pm) {
-          const int p = __ffs(pm) - 1;
-          pm &= pm - 1;
-          const float wyp = __shfl_sync(0xffffffffu, wy, p);
-          const float* grow = gr + (long)p * PW * C;
-          unsigned qq = qall;
-          while (qq) {
-            const int q = __ffs(qq) - 1;
-            qq &= qq - 1;
-            ulonglong2 v = make_ulonglong2(0ull, 0ull);
-            if (active) v = __ldg(reinterpret_cast<const ulonglong2*>(grow + (long)q * C));
-#pragma unroll
-            for (int x = 0; x < TW; x++) {
-              if ((qm[x] >> q) & 1u) {                  // warp-uniform
-                const float w = wyp * __shfl_sync(0xffffffffu, wx[x], q);
-                const u64 w2 = pack2(w, w);
-                acc[x][0] = fma2(w2, v.x, acc[x][0]);
-                acc[x][1] = fma2(w2, v.y, acc[x][1]);
-              }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- the tile's gradient: written exactly once ----
-  if (active && y < H) {
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
-    const long C4 = C >> 2;
-#pragma unroll
-    for (int x = 0; x < TW; x++)
-      if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
-  }
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // deterministic tile-owner gather, staged: the single-pass kernel (no channel-vector copy of grad_out in HBM)
@@ -805,13 +644,23 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 using namespace cpm;
 
 struct BwdWs {
-  size_t seg_count, perm, taps, box, goT, total;
+  size_t seg_count, perm, taps, box, rowclip, tile_count, tile_off, lists, total;
 };
 
 // the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
 static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
-static BwdWs bwd_layout(int64_t K, int L, int B, int C, int PH, int PW, int G) {
+// CPM_BWD_IMPL=staged forces the generic staged kernel (A/B measurements); read once per process
+static bool tma_disabled() {
+  static const bool off = [] {
+    const char* e = getenv("CPM_BWD_IMPL");
+    return e != nullptr && strcmp(e, "staged") == 0;
+  }();
+  return off;
+}
+
+// tiles > 0: with the per-tile candidate lists of the TMA kernel
+static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, long tiles, size_t list_entries, int bands = 0) {
   BwdWs w;
   const size_t segs = (size_t)(L > 0 ? L : 1) * (size_t)(B > 0 ? B : 1);
   const size_t k = (size_t)(K > 0 ? K : 1);
@@ -821,14 +670,31 @@ static BwdWs bwd_layout(int64_t K, int L, int B, int C, int PH, int PW, int G) {
   w.perm = take(segs * k * sizeof(int));
   w.taps = take(k * (size_t)(PH + PW) * (size_t)(G > 0 ? G : 1) * sizeof(TapS));
   w.box = take(k * sizeof(int4));
-  w.goT = take(bwd_staged_ok(PH, PW, G) ? 0 : k * (size_t)C * PH * PW * sizeof(float));
+  w.rowclip = take(tiles > 0 ? k * (size_t)bands * sizeof(int) : 0);
+  w.tile_count = take((size_t)tiles * sizeof(int));
+  w.tile_off = take((size_t)tiles * sizeof(int));
+  w.lists = take(list_entries * sizeof(int2));
   w.total = off;
   return w;
 }
 
+static bool tma_shape_ok(const cpm_pyramid_t* p, int PH, int PW, int G) {
+  return !tma_disabled() && btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0;
+}
+
 extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
                                                          int pooled_w, int sampling_ratio) {
-  return bwd_layout(K, num_levels, batch, channels, pooled_h, pooled_w, sampling_ratio).total;
+  (void)channels;
+  return bwd_layout(K, num_levels, batch, pooled_h, pooled_w, sampling_ratio, 0, 0).total;
+}
+
+extern "C" size_t cpm_roi_align_backward_workspace_bytes_pyr(const cpm_pyramid_t* grad_feat, int64_t K, int pooled_h,
+                                                             int pooled_w, int sampling_ratio) {
+  if (grad_feat == nullptr || grad_feat->num_levels < 1 || grad_feat->num_levels > CPM_MAX_LEVELS) return 0;
+  if (tma_shape_ok(grad_feat, pooled_h, pooled_w, sampling_ratio))
+    return bwd_layout(K, grad_feat->num_levels, grad_feat->batch, pooled_h, pooled_w, sampling_ratio,
+                      btma::num_tiles(grad_feat), btma::list_entries(grad_feat, K, pooled_h), btma::num_bands(grad_feat)).total;
+  return bwd_layout(K, grad_feat->num_levels, grad_feat->batch, pooled_h, pooled_w, sampling_ratio, 0, 0).total;
 }
 
 extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
@@ -848,9 +714,9 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
   CPM_CHECK_ARG(pooled_layout == CPM_POOLED_KCHW || pooled_layout == CPM_POOLED_KHWC, "unknown pooled layout %d", pooled_layout);
   if (pooled_layout == CPM_POOLED_KHWC &&
       !(mode == CPM_BWD_DETERMINISTIC && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio) && grad_feat->channels % 4 == 0 &&
-        ((uintptr_t)d_grad_out & 15) == 0)) {
+        grad_feat->layout == CPM_LAYOUT_NHWC && ((uintptr_t)d_grad_out & 15) == 0)) {
     set_error("a channels-last pooled gradient (CPM_POOLED_KHWC) is read by the deterministic staged kernel only "
-              "(pooled size * sampling_ratio <= 32, C %% 4 == 0, 16-byte aligned grad_out)");
+              "(NHWC gradient pyramid, pooled size * sampling_ratio <= 32, C %% 4 == 0, 16-byte aligned grad_out)");
     return CPM_ERR_UNSUPPORTED;
   }
   CPM_CHECK_ARG(K >= 0, "K < 0");
@@ -882,12 +748,25 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
   const int chunks = (C + kChunk - 1) / kChunk;
 
   if (mode == CPM_BWD_DETERMINISTIC) {
-    if (!(nhwc_f32 && sampling_ratio >= 1 && pooled_h <= kMaxP && pooled_w <= kMaxP)) {
-      set_error("deterministic backward needs an NHWC fp32 gradient pyramid, bilinear interpolation, C %% 4 == 0, "
-                "sampling_ratio >= 1 and pooled size <= %d; use CPM_BWD_ATOMIC otherwise", kMaxP);
+    // the TMA kernel: the two CPM poolers, (K,C,PH,PW) gradient, NHWC or NCHW gradient pyramid
+    bool tma = pooled_layout == CPM_POOLED_KCHW && interpolation == CPM_INTERP_BILINEAR &&
+               tma_shape_ok(grad_feat, pooled_h, pooled_w, sampling_ratio) && ((uintptr_t)d_grad_out & 15) == 0;
+    for (int l = 0; tma && l < L; l++) tma = ((uintptr_t)grad_feat->d_level[l] & 15) == 0;
+    BwdWs w = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, 0, 0);
+    if (tma) {
+      const size_t entries = btma::list_entries(grad_feat, K, pooled_h);
+      const BwdWs wt = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, btma::num_tiles(grad_feat), entries,
+                                  btma::num_bands(grad_feat));
+      if (entries < (1ull << 31) && d_workspace != nullptr && workspace_bytes >= wt.total) w = wt;
+      else tma = false;      // sized with the plain query: the generic staged kernel takes the call
+    }
+    if (!tma && !(nhwc_f32 && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio))) {
+      set_error("deterministic backward: the generic kernel needs an NHWC fp32 gradient pyramid, bilinear interpolation, "
+                "C %% 4 == 0 and pooled size * sampling_ratio <= 32 (sampling_ratio >= 1); the 7x7 / 14x14 sampling_ratio 2 "
+                "poolers with C %% 64 == 0 also take an NCHW pyramid (size the workspace with "
+                "cpm_roi_align_backward_workspace_bytes_pyr); use CPM_BWD_ATOMIC otherwise");
       return CPM_ERR_UNSUPPORTED;
     }
-    const BwdWs w = bwd_layout(K, L, B, C, pooled_h, pooled_w, sampling_ratio);
     if (d_workspace == nullptr || workspace_bytes < w.total) {
       set_error("workspace too small: %zu < %zu bytes", workspace_bytes, w.total);
       return CPM_ERR_WORKSPACE;
@@ -898,47 +777,30 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     int* perm = (int*)(wsb + w.perm);
     TapS* taps = (TapS*)(wsb + w.taps);
     int4* box = (int4*)(wsb + w.box);
-    float* goT = (float*)(wsb + w.goT);
     const int Kp = K > 0 ? (int)K : 1;
-    const int PP = pooled_h * pooled_w;
-    const bool staged = bwd_staged_ok(pooled_h, pooled_w, sampling_ratio);
     if (K > 0) {
       bwd_prepare<<<(unsigned)(L * B + (K + 3) / 4), 256, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w,
                                                                     sampling_ratio, aligned, mp, d_roi_levels, seg_count,
-                                                                    perm, taps, box);
+                                                                    perm, taps, box, tma ? (int*)(wsb + w.rowclip) : nullptr,
+                                                                    tma ? btma::num_bands(grad_feat) : 0);
       CPM_CHECK_LAUNCH();
-      // grad_out (K, C, PP) -> (K, PP, C)  (only the unstaged kernel reads the copy)
-      for (long k0 = 0; k0 < K && !staged; k0 += 32768) {
-        const int kb = (int)((K - k0) < 32768 ? (K - k0) : 32768);
-        dim3 grid((PP + 31) / 32, (C + 31) / 32, kb);
-        transpose_go<float><<<grid, 256, 0, st>>>((const float*)d_grad_out + k0 * (long)C * PP, goT + k0 * (long)C * PP, C, PP);
-        CPM_CHECK_LAUNCH();
-      }
     } else {
       CPM_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, (size_t)L * B * sizeof(int), st));
     }
+    if (tma) {
+      rc = btma::launch(grad_feat, pv, (const float*)d_grad_out, (int)K, pooled_h, taps, box, (const int*)(wsb + w.rowclip),
+                        seg_count, perm, (int*)(wsb + w.tile_count), (int*)(wsb + w.tile_off), (int2*)(wsb + w.lists), st);
+      if (rc != CPM_ERR_UNSUPPORTED || !nhwc_f32) return rc;
+      // no tensor-map encoder in this driver: the generic staged kernel below
+    }
     TileGrid tg;
-    long tiles = 0;
-    for (int i = 0; i < L; i++) {
-      const int l = L - 1 - i;   // coarse levels (many RoIs per tile) first
-      tg.order[i] = l;
-      tg.tiles_x[l] = (grad_feat->width[l] + TW - 1) / TW;
-      tg.tiles_y[l] = (grad_feat->height[l] + TH - 1) / TH;
-      tg.first[i] = (int)tiles;
-      tiles += (long)B * tg.tiles_x[l] * tg.tiles_y[l];
-    }
-    for (int i = L; i <= CPM_MAX_LEVELS; i++) tg.first[i] = (int)tiles;
+    const long tiles = make_tile_grid(tg, grad_feat, TH, TW);
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
-    if (staged) {
-      const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio)
-                                                                : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
-      CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
-      fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
-          pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
-    } else {
-      bwd_tiles<<<(unsigned)(tiles * chunks), kTileThreads, 0, st>>>(pv, tg, goT, taps, box, Kp, pooled_h, pooled_w,
-                                                                    sampling_ratio, seg_count, perm, chunks);
-    }
+    const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio)
+                                                              : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
+    fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
+        pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
     CPM_CHECK_LAUNCH();
     return CPM_OK;
   }

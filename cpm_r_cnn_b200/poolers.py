@@ -14,7 +14,7 @@ from torch.autograd.function import once_differentiable
 from torch.nn.modules.utils import _pair
 
 from . import _lib
-from .roi_align import INTERPOLATION_METHOD, ROIAlign, _float_function, pooler_backward, pooler_forward
+from .roi_align import INTERPOLATION_METHOD, ROIAlign, _float_function, _is_nhwc, pooler_backward, pooler_forward
 
 
 class LevelMapper(object):
@@ -56,6 +56,7 @@ class _PyramidROIAlign(Function):
         ctx.save_for_backward(rois)
         ctx.cfg = cfg
         ctx.shapes = [tuple(t.shape) for t in levels]
+        ctx.nchw_input = not all(_is_nhwc(t) for t in levels)
         output_size, scales, sampling_ratio, aligned, interp, mapper, channels_last = cfg
         return pooler_forward(list(levels), scales, rois, output_size, sampling_ratio, aligned, interp, mapper,
                               channels_last=channels_last)
@@ -66,7 +67,7 @@ class _PyramidROIAlign(Function):
         rois, = ctx.saved_tensors
         output_size, scales, sampling_ratio, aligned, interp, mapper, _ = ctx.cfg
         grads = pooler_backward(grad_output, ctx.shapes, scales, rois, output_size, sampling_ratio, aligned, interp,
-                                mapper)
+                                mapper, nchw_grad=ctx.nchw_input)
         return (None, None) + tuple(grads)
 
 

@@ -112,41 +112,71 @@ def pooler_forward(levels, scales, rois, output_size, sampling_ratio, aligned, i
     return out
 
 
+_WARNED = set()
+
+
+def _warn_once(key, msg):
+    if key not in _WARNED:
+        _WARNED.add(key)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
+def _tma_pooler(ph, pw, sampling_ratio, C, dt, interpolation):
+    """The poolers the warp-specialised TMA backward takes (csrc/roi_align_bwd_tma.cu)."""
+    return (dt == torch.float32 and interpolation == 0 and C % 64 == 0 and ph == pw and ph in (7, 14)
+            and int(sampling_ratio) == 2 and os.environ.get("CPM_BWD_IMPL", "") != "staged")
+
+
 def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper,
-                    mode=None):
-    """Dense gradients of every level: list[(B,C,H_l,W_l)] (channels_last strides on the NHWC path)."""
+                    mode=None, nchw_grad=False):
+    """Dense gradients of every level: list[(B,C,H_l,W_l)].
+
+    nchw_grad=True (the forward was fed NCHW-contiguous maps, what the reference's FPN emits) asks for NCHW-contiguous
+    gradients, the layout _C.roi_align_backward returns (ROIAlign_cuda.cu:451-452); the TMA kernel of the two CPM poolers
+    writes them directly.  Otherwise (and for every other pooler) the fast kernels write NHWC and the tensors come
+    back with channels_last strides."""
     _lib.require_cuda(grad_output, "grad_output")
     mode = BACKWARD_MODE if mode is None else mode
+    if mode not in ("deterministic", "atomic"):
+        raise ValueError("cpm_ops: CPM_ROI_ALIGN_BACKWARD / mode must be 'deterministic' or 'atomic' (got %r)" % (mode,))
     if grad_output.dtype == torch.bfloat16:
         # bf16 pooled gradient (native bf16 forward): accumulate the dense gradient in fp32, round once at the end
         grads = pooler_backward(grad_output.float(), shapes, scales, rois, output_size, sampling_ratio, aligned,
-                                interpolation, mapper, mode)
+                                interpolation, mapper, mode, nchw_grad)
         return [g.to(torch.bfloat16) for g in grads]
     ph, pw = output_size
     K = rois.shape[0]
     dt, dev = grad_output.dtype, grad_output.device
     B, C = shapes[0][0], shapes[0][1]
     nhwc = dt == torch.float32 and interpolation == 0 and C % 4 == 0
-    fmt = torch.channels_last if nhwc else torch.contiguous_format
-    grads = [torch.empty(tuple(s), dtype=dt, device=dev, memory_format=fmt) for s in shapes]
-    if B == 0 or any(g.numel() == 0 for g in grads):
-        return grads
-    pyr = make_pyramid(grads, scales, _lib.NHWC if nhwc else _lib.NCHW)
-    rois = rois.contiguous()
-    det_ok = nhwc and sampling_ratio >= 1 and ph <= 32 and pw <= 32
-    use = _lib.BWD_DETERMINISTIC if (mode == "deterministic" and det_ok) else _lib.BWD_ATOMIC
+    staged = nhwc and sampling_ratio >= 1 and ph * sampling_ratio <= 32 and pw * sampling_ratio <= 32
+    if mode == "deterministic" and not staged:
+        _warn_once(("det", ph, pw, int(sampling_ratio), str(dt), interpolation),
+                   "cpm_ops: the deterministic RoIAlign backward needs fp32, bilinear interpolation, C % 4 == 0 and "
+                   "1 <= sampling_ratio with pooled size * sampling_ratio <= 32; this call uses the atomic "
+                   "(order-non-deterministic) scatter instead")
+    use = _lib.BWD_DETERMINISTIC if (mode == "deterministic" and staged) else _lib.BWD_ATOMIC
     # a channels_last-strided pooled gradient (what a channels_last conv head hands back) is read in place by the staged
     # kernel; anything else is taken in the reference's (K,C,PH,PW) order
-    staged = use == _lib.BWD_DETERMINISTIC and ph * sampling_ratio <= 32 and pw * sampling_ratio <= 32
-    khwc = (staged and K > 0 and ph * pw > 1 and C > 1 and not grad_output.is_contiguous()
+    khwc = (use == _lib.BWD_DETERMINISTIC and K > 0 and ph * pw > 1 and C > 1 and not grad_output.is_contiguous()
             and grad_output.is_contiguous(memory_format=torch.channels_last) and grad_output.data_ptr() % 16 == 0)
     if not khwc:
         grad_output = grad_output.contiguous()
+    tma = use == _lib.BWD_DETERMINISTIC and not khwc and _tma_pooler(ph, pw, sampling_ratio, C, dt, interpolation)
+    out_nchw = (not nhwc) or (nchw_grad and tma)
+    fmt = torch.contiguous_format if out_nchw else torch.channels_last
+    grads = [torch.empty(tuple(s), dtype=dt, device=dev, memory_format=fmt) for s in shapes]
+    if B == 0 or any(g.numel() == 0 for g in grads):
+        return grads
+    pyr = make_pyramid(grads, scales, _lib.NCHW if out_nchw else _lib.NHWC)
+    rois = rois.contiguous()
     layout = _lib.POOLED_KHWC if khwc else _lib.POOLED_KCHW
     ws, ws_bytes = None, 0
     with _lib.device_of(grad_output):
         if use == _lib.BWD_DETERMINISTIC:
-            ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes(K, len(shapes), B, C, ph, pw, int(sampling_ratio)))
+            ws_bytes = int(_lib.lib().cpm_roi_align_backward_workspace_bytes_pyr(ctypes.byref(pyr), K, ph, pw,
+                                                                                 int(sampling_ratio)))
             ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         _lib.check(_lib.lib().cpm_roi_align_backward_ex(ctypes.byref(pyr), _lib.ptr(grad_output), _lib.ptr(rois), K, ph, pw,
                                                         int(sampling_ratio), int(bool(aligned)), interpolation,
@@ -169,6 +199,7 @@ class _ROIAlign(Function):
         ctx.input_shape = input.size()
         ctx.aligned = aligned
         ctx.interpolation_method = INTERPOLATION_METHOD[interpolation]
+        ctx.nchw_input = not _is_nhwc(input)
         return pooler_forward([input], [spatial_scale], roi, ctx.output_size, sampling_ratio, aligned,
                               ctx.interpolation_method, None, channels_last=_ROIAlign.pooled_channels_last)
 
@@ -177,7 +208,8 @@ class _ROIAlign(Function):
     def backward(ctx, grad_output):
         rois, = ctx.saved_tensors
         grad_input = pooler_backward(grad_output, [ctx.input_shape], [ctx.spatial_scale], rois, ctx.output_size,
-                                     ctx.sampling_ratio, ctx.aligned, ctx.interpolation_method, None)[0]
+                                     ctx.sampling_ratio, ctx.aligned, ctx.interpolation_method, None,
+                                     nchw_grad=ctx.nchw_input)[0]
         return grad_input, None, None, None, None, None, None
 
 
