@@ -617,11 +617,38 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
 
   // ---- the tile's gradient: written exactly once ----
   if (active && y < H) {
-    ulonglong2* dst = reinterpret_cast<ulonglong2*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
-    const long C4 = C >> 2;
+    if (pv.layout == CPM_LAYOUT_NCHW) {
+      // the reference's gradient layout (ROIAlign_cuda.cu:451-452): a lane owns 4 channel planes, in each 8 consecutive
+      // columns of row y -- one 32-byte sector per (lane, channel)
+      float* dst = (float*)pv.ptr[l] + (((long)b * C + c0 + 4 * lane) * H + y) * W + x0;
+      const long cs = (long)H * W;
+      const bool v4 = (W & 3) == 0 && x0 + TW <= W;
 #pragma unroll
-    for (int x = 0; x < TW; x++)
-      if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
+      for (int j = 0; j < 4; j++) {
+        float v[TW];
+#pragma unroll
+        for (int x = 0; x < TW; x++) {
+          float lo, hi;
+          unpack2(acc[x][j >> 1], lo, hi);
+          v[x] = (j & 1) ? hi : lo;
+        }
+        float* row = dst + j * cs;
+        if (v4) {
+          reinterpret_cast<float4*>(row)[0] = make_float4(v[0], v[1], v[2], v[3]);
+          reinterpret_cast<float4*>(row)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+          for (int x = 0; x < TW; x++)
+            if (x0 + x < W) row[x] = v[x];
+        }
+      }
+    } else {
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>((float*)pv.ptr[l] + (((long)b * H + y) * W + x0) * C + c0) + lane;
+      const long C4 = C >> 2;
+#pragma unroll
+      for (int x = 0; x < TW; x++)
+        if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
+    }
   }
 }
 
@@ -650,13 +677,14 @@ struct BwdWs {
 // the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
 static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
-// CPM_BWD_IMPL=staged forces the generic staged kernel (A/B measurements); read once per process
-static bool tma_disabled() {
-  static const bool off = [] {
+// CPM_BWD_IMPL=tma selects the warp-specialised TMA tile kernel for the two CPM poolers (measured slower than the staged
+// kernel on the benchmark workload, DESIGN.md section 7: kept for A/B measurements); read once per process
+static bool tma_enabled() {
+  static const bool on = [] {
     const char* e = getenv("CPM_BWD_IMPL");
-    return e != nullptr && strcmp(e, "staged") == 0;
+    return e != nullptr && strcmp(e, "tma") == 0;
   }();
-  return off;
+  return on;
 }
 
 // tiles > 0: with the per-tile candidate lists of the TMA kernel
@@ -679,7 +707,7 @@ static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, long til
 }
 
 static bool tma_shape_ok(const cpm_pyramid_t* p, int PH, int PW, int G) {
-  return !tma_disabled() && btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0;
+  return tma_enabled() && btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0;
 }
 
 extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
@@ -714,9 +742,9 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
   CPM_CHECK_ARG(pooled_layout == CPM_POOLED_KCHW || pooled_layout == CPM_POOLED_KHWC, "unknown pooled layout %d", pooled_layout);
   if (pooled_layout == CPM_POOLED_KHWC &&
       !(mode == CPM_BWD_DETERMINISTIC && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio) && grad_feat->channels % 4 == 0 &&
-        grad_feat->layout == CPM_LAYOUT_NHWC && ((uintptr_t)d_grad_out & 15) == 0)) {
+        ((uintptr_t)d_grad_out & 15) == 0)) {
     set_error("a channels-last pooled gradient (CPM_POOLED_KHWC) is read by the deterministic staged kernel only "
-              "(NHWC gradient pyramid, pooled size * sampling_ratio <= 32, C %% 4 == 0, 16-byte aligned grad_out)");
+              "(pooled size * sampling_ratio <= 32, C %% 4 == 0, 16-byte aligned grad_out)");
     return CPM_ERR_UNSUPPORTED;
   }
   CPM_CHECK_ARG(K >= 0, "K < 0");
@@ -742,9 +770,10 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
   const size_t esz = grad_feat->dtype == CPM_F64 ? 8 : 4;
   if (B == 0) return CPM_OK;
 
-  bool nhwc_f32 = grad_feat->layout == CPM_LAYOUT_NHWC && grad_feat->dtype == CPM_F32 &&
-                  interpolation == CPM_INTERP_BILINEAR && C % 4 == 0;
-  for (int l = 0; nhwc_f32 && l < L; l++) nhwc_f32 = ((uintptr_t)grad_feat->d_level[l] & 15) == 0;
+  // what the fast kernels need of the gradient pyramid: fp32, bilinear, channel vectors of 4, 16-byte aligned levels
+  bool fast_f32 = grad_feat->dtype == CPM_F32 && interpolation == CPM_INTERP_BILINEAR && C % 4 == 0;
+  for (int l = 0; fast_f32 && l < L; l++) fast_f32 = ((uintptr_t)grad_feat->d_level[l] & 15) == 0;
+  const bool nhwc_f32 = fast_f32 && grad_feat->layout == CPM_LAYOUT_NHWC;
   const int chunks = (C + kChunk - 1) / kChunk;
 
   if (mode == CPM_BWD_DETERMINISTIC) {
@@ -760,11 +789,10 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
       if (entries < (1ull << 31) && d_workspace != nullptr && workspace_bytes >= wt.total) w = wt;
       else tma = false;      // sized with the plain query: the generic staged kernel takes the call
     }
-    if (!tma && !(nhwc_f32 && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio))) {
-      set_error("deterministic backward: the generic kernel needs an NHWC fp32 gradient pyramid, bilinear interpolation, "
-                "C %% 4 == 0 and pooled size * sampling_ratio <= 32 (sampling_ratio >= 1); the 7x7 / 14x14 sampling_ratio 2 "
-                "poolers with C %% 64 == 0 also take an NCHW pyramid (size the workspace with "
-                "cpm_roi_align_backward_workspace_bytes_pyr); use CPM_BWD_ATOMIC otherwise");
+    if (!tma && !(fast_f32 && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio))) {
+      set_error("deterministic backward needs an fp32 gradient pyramid (NHWC or NCHW, 16-byte aligned levels), bilinear "
+                "interpolation, C %% 4 == 0 and pooled size * sampling_ratio <= 32 (sampling_ratio >= 1); use "
+                "CPM_BWD_ATOMIC otherwise");
       return CPM_ERR_UNSUPPORTED;
     }
     if (d_workspace == nullptr || workspace_bytes < w.total) {
@@ -790,7 +818,7 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     if (tma) {
       rc = btma::launch(grad_feat, pv, (const float*)d_grad_out, (int)K, pooled_h, taps, box, (const int*)(wsb + w.rowclip),
                         seg_count, perm, (int*)(wsb + w.tile_count), (int*)(wsb + w.tile_off), (int2*)(wsb + w.lists), st);
-      if (rc != CPM_ERR_UNSUPPORTED || !nhwc_f32) return rc;
+      if (rc != CPM_ERR_UNSUPPORTED) return rc;
       // no tensor-map encoder in this driver: the generic staged kernel below
     }
     TileGrid tg;

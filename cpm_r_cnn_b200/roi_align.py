@@ -122,20 +122,13 @@ def _warn_once(key, msg):
         warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
 
-def _tma_pooler(ph, pw, sampling_ratio, C, dt, interpolation):
-    """The poolers the warp-specialised TMA backward takes (csrc/roi_align_bwd_tma.cu)."""
-    return (dt == torch.float32 and interpolation == 0 and C % 64 == 0 and ph == pw and ph in (7, 14)
-            and int(sampling_ratio) == 2 and os.environ.get("CPM_BWD_IMPL", "") != "staged")
-
-
 def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_ratio, aligned, interpolation, mapper,
                     mode=None, nchw_grad=False):
     """Dense gradients of every level: list[(B,C,H_l,W_l)].
 
     nchw_grad=True (the forward was fed NCHW-contiguous maps, what the reference's FPN emits) asks for NCHW-contiguous
-    gradients, the layout _C.roi_align_backward returns (ROIAlign_cuda.cu:451-452); the TMA kernel of the two CPM poolers
-    writes them directly.  Otherwise (and for every other pooler) the fast kernels write NHWC and the tensors come
-    back with channels_last strides."""
+    gradients, the layout _C.roi_align_backward returns (ROIAlign_cuda.cu:451-452): the deterministic tile kernels write
+    them directly.  Otherwise the fast kernels write NHWC and the tensors come back with channels_last strides."""
     _lib.require_cuda(grad_output, "grad_output")
     mode = BACKWARD_MODE if mode is None else mode
     if mode not in ("deterministic", "atomic"):
@@ -163,8 +156,7 @@ def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_rat
             and grad_output.is_contiguous(memory_format=torch.channels_last) and grad_output.data_ptr() % 16 == 0)
     if not khwc:
         grad_output = grad_output.contiguous()
-    tma = use == _lib.BWD_DETERMINISTIC and not khwc and _tma_pooler(ph, pw, sampling_ratio, C, dt, interpolation)
-    out_nchw = (not nhwc) or (nchw_grad and tma)
+    out_nchw = (not nhwc) or (nchw_grad and use == _lib.BWD_DETERMINISTIC)
     fmt = torch.contiguous_format if out_nchw else torch.channels_last
     grads = [torch.empty(tuple(s), dtype=dt, device=dev, memory_format=fmt) for s in shapes]
     if B == 0 or any(g.numel() == 0 for g in grads):

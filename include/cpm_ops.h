@@ -130,10 +130,10 @@ CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois,
  * which the single-pass staged kernel does not take, a channel-vector copy (K, PH*PW, C) of grad_out). */
 CPM_API size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
                                                       int pooled_w, int sampling_ratio);
-/* The same query given the gradient pyramid itself (shapes, dtype): for the two CPM poolers (7x7 / 14x14, sampling_ratio 2,
- * C % 64 == 0, fp32) the size includes the per-tile candidate lists of the TMA tile kernel, which also writes an NCHW
- * gradient pyramid (the layout _C.roi_align_backward returns, ROIAlign_cuda.cu:451-452) directly.  A workspace sized with
- * the plain query above is served by the generic staged kernel (NHWC pyramids only). */
+/* The same query given the gradient pyramid itself (shapes, dtype); what the Python layer calls.  Equal to the plain query
+ * unless the experimental TMA tile kernel is selected (CPM_BWD_IMPL=tma: 7x7 / 14x14 poolers, sampling_ratio 2, C % 64 == 0,
+ * fp32), whose per-tile stage lists it adds.  Both deterministic kernels write an NHWC or an NCHW gradient pyramid (the
+ * layout _C.roi_align_backward returns, ROIAlign_cuda.cu:451-452). */
 CPM_API size_t cpm_roi_align_backward_workspace_bytes_pyr(const cpm_pyramid_t* grad_feat, int64_t K, int pooled_h, int pooled_w,
                                                           int sampling_ratio);
 CPM_API int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
