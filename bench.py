@@ -26,10 +26,18 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of each op's main kernel, from the committed `ncu --set full`
-# capture of this same workload (profiles/ncu_r01_summary.txt); not re-measured by bench.py (a run under ncu is never timed)
-NCU_DRAM_BYTES = {"fwd7": 157.1e6, "fwd14": 316.0e6, "bwd7": 177.5e6, "bwd14": 361.2e6}
-NCU_DRAM_SOURCE = "profiles/ncu_r01_summary.txt (ncu --set full, one capture per kernel)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of each op's main kernel come from the committed digest of the
+# `ncu --set full` capture of this same workload (written by tools/ncu_digest.py --json); a run under ncu is never timed,
+# so bench.py only READS the file -- absent or stale (kernel name mismatch) => traffic is null
+NCU_DRAM_FILE = os.path.join(ROOT, "profiles", "ncu_dram_r02.json")
+
+
+def ncu_dram_bytes():
+    try:
+        return json.load(open(NCU_DRAM_FILE))
+    except Exception:
+        return {}
+
 
 METRIC = "roi_align_fwd_bwd_rois_per_sec"
 UNIT = "RoIs/s"
@@ -162,12 +170,15 @@ def cpu_reference_rate(sample_rois_per_img=48):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU RoIAlign (unmodified ROIAlign_cpu.cpp, single-threaded by construction)
+    on the SAME workload as the repo arm: every step pools all 512 RoIs/img of both images through both poolers, forward
+    + backward.  Rank 0 alone runs it (one host core = one process); the line therefore says n_gpus 1 whatever --gpus is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rates, times = [], []
-    # each step is a bounded sample sized so that the whole run stays within ~2 minutes of single-thread CPU work
-    n_step = min(ROIS_PER_IMG, max(8, 3000 // max(args.steps, 1)))
+    # one full step is ~4.5 s of single-thread CPU work; only a run asked for more than 40 steps is sampled down
+    n_step = ROIS_PER_IMG if args.steps <= 40 else max(8, (40 * ROIS_PER_IMG) // args.steps)
     for i in range(args.warmup + args.steps):
         n = 8 if i < args.warmup else n_step
         r, dt, kind, sample = cpu_reference_rate(n)
@@ -175,11 +186,14 @@ def run_reference(args):
             rates.append(r)
             times.append(dt)
     value = sum(rates) / len(rates)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "requested_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: R-50-FPN CPM head RoIAlign 7x7 + 14x14 fwd+bwd, 2 img, 512 RoIs/img, "
-                                   "256 ch fp32 (bounded sample per step)", "sample": sample},
+            "config": {"workload": "configs[1]: R-50-FPN CPM head RoIAlign 7x7 + 14x14 fwd+bwd, %d img/GPU, %d RoIs/img, "
+                                   "4-level 256-ch fp32 pyramid of 800x1344 images, sampling_ratio 2" % (IMGS_PER_GPU, ROIS_PER_IMG),
+                       "sample": sample, "same_workload_as_repo_arm": n_step == ROIS_PER_IMG,
+                       "note": "one CPU process on rank 0 (the kernel is single-threaded: ROIAlign_cpu.cpp:185-186 has its omp "
+                               "pragma commented out); compare with the repo arm at N = 1"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -189,10 +203,170 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_cores(index):
+    """Pins this process to the CPU cores NVML reports as local to GPU `index` (before any pinned allocation, so that the
+    staging buffers are first-touched on that NUMA node).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"cpus": "%d-%d (%d)" % (allowed[0], allowed[-1], len(allowed)) if allowed else None}
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:120]}
+
+
+def capture(fn):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = fn()
+    return g, keep
+
+
+def time_graphs(graphs, iters, skip=2):
+    """Median per-graph time (ms) over `iters` passes of the graph list, CUDA events on the launching stream."""
+    n = len(graphs)
+    rec = [[] for _ in range(n)]
+    for it in range(iters + skip):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        for j, g in enumerate(graphs):
+            e[j].record()
+            g.replay()
+        e[n].record()
+        torch.cuda.synchronize()
+        if it >= skip:
+            for j in range(n):
+                rec[j].append(e[j].elapsed_time(e[j + 1]))
+    return [sorted(r)[len(r) // 2] for r in rec]
+
+
+def reference_levels(rois):
+    """LevelMapper with the reference's torch expressions (pet/rcnn/utils/poolers.py:29-40, k_min 2, k_max 5)."""
+    area = (rois[:, 3] - rois[:, 1] + 1) * (rois[:, 4] - rois[:, 2] + 1)
+    lv = torch.floor(4 + torch.log2(torch.sqrt(area) / 224 + 1e-6))
+    return torch.clamp(lv, min=2, max=5).to(torch.int64) - 2
+
+
+def reference_gpu_roi_align(feats_nchw, rois, gouts, scales, iters=5):
+    """The reference's own single-GPU path for the same step, timed with CUDA events in this process: the UNMODIFIED
+    ROIAlign_cuda.cu (oracle/_ref/pet_ref_cuda.so) through the reference Pooler's per-level loop -- LevelMapper in torch
+    ops, nonzero() per level (host sync), _C.roi_align_forward per level (which ends in cudaDeviceSynchronize,
+    ROIAlign_cuda.cu:422), index assignment (poolers.py:117-131) -- and the matching autograd backward: the index
+    gather of the pooled gradient and one _C.roi_align_backward (at::zeros + atomicAdd scatter) per level."""
+    out = {}
+    try:
+        from oracle import build_ref
+        ref = build_ref.load("pet_ref_cuda")
+        K, C = rois.shape[0], feats_nchw[0].shape[1]
+
+        def fwd(p):
+            lv = reference_levels(rois)
+            res = torch.zeros((K, C, p[0], p[1]), dtype=feats_nchw[0].dtype, device=rois.device)
+            for l, f in enumerate(feats_nchw):
+                idx = torch.nonzero(lv == l).squeeze(1)
+                res[idx] = ref.roi_align_forward(f, rois[idx], scales[l], p[0], p[1], SAMPLING, False, 0)
+            return res
+
+        def bwd(p, go):
+            lv = reference_levels(rois)
+            grads = []
+            for l, f in enumerate(feats_nchw):
+                idx = torch.nonzero(lv == l).squeeze(1)
+                B, _, H, W = f.shape
+                grads.append(ref.roi_align_backward(go[idx].contiguous(), rois[idx], scales[l], p[0], p[1], B, C, H, W,
+                                                    SAMPLING, False, 0))
+            return grads
+
+        fns = []
+        for p, go in zip(POOLERS, gouts):
+            fns += [(lambda p=p: fwd(p)), (lambda p=p, go=go: bwd(p, go))]
+        for fn in fns:
+            fn()
+        torch.cuda.synchronize()
+        ms = [0.0] * 4
+        for it in range(iters):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            for j, fn in enumerate(fns):
+                e[j].record()
+                fn()
+            e[4].record()
+            torch.cuda.synchronize()
+            for j in range(4):
+                ms[j] += e[j].elapsed_time(e[j + 1]) / iters
+        out = {"op": "unmodified ROIAlign_cuda.cu (pet_ref_cuda.so) through the reference Pooler's per-level loop, NCHW fp32",
+               "ms": dict(zip(["fwd7", "bwd7", "fwd14", "bwd14"], ms)), "ms_per_step": sum(ms),
+               "rois_per_sec": K * len(POOLERS) / (sum(ms) * 1e-3)}
+    except Exception as ex:
+        out = {"unavailable": repr(ex)[:200]}
+    return out
+
+
+def bench_config0(dev):
+    """configs[0]: ROIAlign 7x7 forward on ONE synthetic 800x1333 (padded 800x1344) R-50-FPN image, 512 RoIs, 256 channels:
+    the reference's CPU kernel through the per-level loop (1 thread by construction) and torchvision's CPU roi_align
+    (all torch threads) beside the GPU op on the same inputs."""
+    from cpm_r_cnn_b200 import _lib, synthetic as sy
+    from cpm_r_cnn_b200.roi_align import pooler_forward
+    res = {}
+    gen = torch.Generator().manual_seed(0)
+    rois = sy.coco_like_rois(gen, 512, 1)
+    feats = sy.pyramid(gen, 1, CHANNELS)
+    lv = sy.fpn_levels_host(rois)
+    scales = list(sy.FPN_SCALES)
+    mapper = _lib.make_mapper(2, 5)
+    fd = [f.to(dev) for f in feats]
+    rd = rois.to(dev)
+    fn = lambda: pooler_forward(fd, scales, rd, (7, 7), SAMPLING, False, 0, mapper)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g, keep = capture(fn)
+    ms = time_graphs([g], 10)[0]
+    res["ours_gpu"] = {"ms": ms, "rois_per_sec": 512 / (ms * 1e-3),
+                       "note": "NCHW input: the graph holds the NHWC staging of the pyramid + the forward kernel"}
+    out_gpu = keep.cpu()
+    try:
+        from oracle import build_ref
+        ref = build_ref.load("pet_ref_cpu")
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        out = torch.zeros((512, CHANNELS, 7, 7))
+        for l, f in enumerate(feats):
+            idx = torch.nonzero(lv == l).squeeze(1)
+            out[idx] = ref.roi_align_forward(f, rois[idx].contiguous(), scales[l], 7, 7, SAMPLING, False, 0)
+        dt = time.perf_counter() - t0
+        rms = float(out.pow(2).mean().sqrt())
+        res["reference_cpu"] = {"ms": dt * 1e3, "rois_per_sec": 512 / dt, "cores": 1, "kind": "reference",
+                                "max_abs_diff_vs_gpu": float((out - out_gpu).abs().max()),
+                                "within_1e-5_rel": bool(((out - out_gpu).abs() <= 1e-5 * (out.abs() + rms)).all())}
+        res["speedup_vs_reference_cpu"] = dt * 1e3 / ms
+    except Exception as ex:
+        res["reference_cpu"] = {"unavailable": repr(ex)[:200]}
+    try:
+        import torchvision
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        for l, f in enumerate(feats):
+            idx = torch.nonzero(lv == l).squeeze(1)
+            torchvision.ops.roi_align(f, rois[idx].contiguous(), (7, 7), scales[l], SAMPLING, False)
+        dt = time.perf_counter() - t0
+        res["torchvision_cpu"] = {"ms": dt * 1e3, "rois_per_sec": 512 / dt, "cores": torch.get_num_threads()}
+    except Exception as ex:
+        res["torchvision_cpu"] = {"unavailable": repr(ex)[:200]}
+    return res
+
+
 def run_ours(args):
     import torch.distributed as dist
     import cpm_r_cnn_b200 as ops
+    import importlib
     from cpm_r_cnn_b200 import _lib, sharding, synthetic as sy
+    ra = importlib.import_module("cpm_r_cnn_b200.roi_align")    # the package re-exports a function of the same name
     from cpm_r_cnn_b200.roi_align import pooler_backward, pooler_forward
 
     rank = int(os.environ.get("RANK", "0"))
@@ -200,6 +374,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the cpm_ops path has no CPU fallback")
+    affinity = bind_to_gpu_cores(local)       # before CUDA / pinned allocations: NUMA-local staging buffers
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # stdout carries exactly one line, the JSON: everything libraries print while the job runs (NCCL writes its version
@@ -211,28 +386,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    skip = os.environ.get("CPM_BENCH_SKIP", "")
 
     rois_h, feats_h, gouts_h = make_workload(rank)
     shapes = [tuple(f.shape) for f in feats_h]
     scales = list(sy.FPN_SCALES)
     mapper = _lib.make_mapper(2, 5)
     K = rois_h.shape[0]
-    # device-resident inputs: channels_last pyramid (the layout a channels_last backbone/FPN emits; zero-copy NHWC)
-    feats = [f.to(dev).contiguous(memory_format=torch.channels_last) for f in feats_h]
     rois = rois_h.to(dev)
     gouts = [g.to(dev) for g in gouts_h]
-
-    # The step is captured once into four CUDA graphs (one per op, through the Python op layer) and replayed: the ops are
-    # tens of microseconds each, so an eager Python loop would time the host's enqueue rate, not the kernels.
-    def op_fwd(p):
-        return lambda: pooler_forward(feats, scales, rois, p, SAMPLING, False, 0, mapper)
-
-    def op_bwd(p, go):
-        return lambda: pooler_backward(go, shapes, scales, rois, p, SAMPLING, False, 0, mapper)
-
-    op_fns = []
-    for p, go in zip(POOLERS, gouts):
-        op_fns += [op_fwd(p), op_bwd(p, go)]
+    # what the reference's FPN hands the Pooler: NCHW-contiguous maps (FPN.py:96-121) ...
+    feats_nchw = [f.to(dev) for f in feats_h]
+    # ... and the same maps as a channels_last backbone would emit them (zero-copy NHWC for the kernels)
+    feats = [f.contiguous(memory_format=torch.channels_last) for f in feats_nchw]
     names = ["fwd7", "bwd7", "fwd14", "bwd14"]
 
     def sync_all():
@@ -241,86 +407,108 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            for fn in op_fns:
-                fn()
-    torch.cuda.current_stream(dev).wait_stream(side)
-    sync_all()
-    graphs, keep, launches_per_step = [], [], 0
-    for fn in op_fns:
-        g = torch.cuda.CUDAGraph()
-        l0 = _lib.launch_count()
-        with torch.cuda.graph(g):
-            keep.append(fn())
-        launches_per_step += _lib.launch_count() - l0
-        graphs.append(g)
 
-    def step(evs=None):
-        for j, g in enumerate(graphs):
-            if evs: evs[j].record()
-            g.replay()
-        if evs: evs[len(graphs)].record()
+    def warm(fns, n=3):
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(n):
+                for fn in fns:
+                    fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        sync_all()
 
+    # ---- HEADLINE: the step as the unmodified reference model feeds it -- NCHW maps in, NCHW gradients out.  The NHWC
+    #      staging of the pyramid is INSIDE the timed region, once per step (the staging cache serves the second pooler,
+    #      as it serves poolers 2..5 of a CPM iteration); everything is captured once in ONE CUDA graph through the Python
+    #      op layer and replayed, because the ops are tens of microseconds each ----
+    def step_nchw():
+        ra.STAGING_CACHE.clear()
+        keep = []
+        for p, go in zip(POOLERS, gouts):
+            keep.append(pooler_forward(feats_nchw, scales, rois, p, SAMPLING, False, 0, mapper))
+            keep.append(pooler_backward(go, shapes, scales, rois, p, SAMPLING, False, 0, mapper, nchw_grad=True))
+        return keep
+
+    warm([step_nchw])
+    l0 = _lib.launch_count()
+    g_step, keep_step = capture(step_nchw)
+    launches_per_step = _lib.launch_count() - l0
+    assert all(t.is_contiguous() for t in keep_step[1]) and all(t.is_contiguous() for t in keep_step[3])
     for _ in range(max(args.warmup, 3)):
-        step()
+        g_step.replay()
     sync_all()
     sampler = ClockSampler(local)
-    if rank == 0 and "clocks" not in os.environ.get("CPM_BENCH_SKIP", ""):
+    if rank == 0 and "clocks" not in skip:
         sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
-    sync_all()
-    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_beg.record()
-    for i in range(args.steps):
-        step(evs[i])
-    t_end.record()
-    sync_all()
-    launches = launches_per_step * args.steps
+    # the contract's K-step region, repeated: the median repeat is the value (a 10 ms region is at the mercy of one hiccup)
+    repeats = []
+    n_rep = 5
+    for _ in range(n_rep):
+        sync_all()
+        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_beg.record()
+        for i in range(args.steps):
+            g_step.replay()
+        t_end.record()
+        sync_all()
+        repeats.append(t_beg.elapsed_time(t_end) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
+    sec_med = sorted(repeats)[n_rep // 2]
     # whole-job figure: units of all ranks / the slowest rank's device time (cpm_r_cnn_b200/sharding.py)
-    units_total, sec_total, value = sharding.aggregate(K * len(POOLERS) * args.steps, t_beg.elapsed_time(t_end) * 1e-3)
+    units_total, sec_total, value = sharding.aggregate(K * len(POOLERS) * args.steps, sec_med)
     ms_step = sec_total * 1e3 / args.steps
     units_per_step = K * len(POOLERS) * world
-    op_ms = {n: sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i, n in enumerate(names)}
 
-    # ---- the same four ops with channels_last pooled tensors (extension, not part of `value`): the forward returns the
-    #      pooled block with channels_last strides and the backward reads a channels_last gradient in place ----
+    # ---- per-op times: pyramid resident as channels_last (NHWC, zero-copy), one graph per op ----
+    def op_fwd(p, cl=False):
+        return lambda: pooler_forward(feats, scales, rois, p, SAMPLING, False, 0, mapper, channels_last=cl)
+
+    def op_bwd(p, go, **kw):
+        return lambda: pooler_backward(go, shapes, scales, rois, p, SAMPLING, False, 0, mapper, **kw)
+
+    op_fns = []
+    for p, go in zip(POOLERS, gouts):
+        op_fns += [op_fwd(p), op_bwd(p, go)]
+    warm(op_fns)
+    caps = [capture(fn) for fn in op_fns]
+    n_it = max(5, min(args.steps, 30))
+    op_list = time_graphs([c[0] for c in caps], n_it)
+    op_ms = dict(zip(names, op_list))
+    if world > 1:
+        t = torch.tensor(op_list, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        op_ms = dict(zip(names, [float(v) for v in t.tolist()]))
+    del caps
+
+    # ---- pieces of the NCHW step, one graph each: the staging alone, the backward writing NCHW ----
+    nchw_ms = {}
+    try:
+        st_fn = lambda: [ra.stage_nhwc(f, cache=False) for f in feats_nchw]
+        b_fns = [op_bwd(p, go, nchw_grad=True) for p, go in zip(POOLERS, gouts)]
+        warm([st_fn] + b_fns, 2)
+        caps = [capture(fn) for fn in [st_fn] + b_fns]
+        t = time_graphs([c[0] for c in caps], n_it)
+        nchw_ms = {"stage_pyramid_nhwc": t[0], "bwd7_nchw_out": t[1], "bwd14_nchw_out": t[2]}
+        del caps
+    except Exception as ex:
+        nchw_ms = {"error": repr(ex)[:200]}
+    sync_all()
+
+    # ---- the same four ops with channels_last pooled tensors (extension): the forward returns the pooled block with
+    #      channels_last strides and the backward reads a channels_last gradient in place ----
     cl_ms = {}
     try:
-        if "cl" in os.environ.get("CPM_BENCH_SKIP", ""):
+        if "cl" in skip:
             raise RuntimeError("skipped")
         gouts_cl = [g.contiguous(memory_format=torch.channels_last) for g in gouts]
         cl_fns = []
         for p, go in zip(POOLERS, gouts_cl):
-            cl_fns += [(lambda p=p: pooler_forward(feats, scales, rois, p, SAMPLING, False, 0, mapper, channels_last=True)),
-                       op_bwd(p, go)]
-        with torch.cuda.stream(side):
-            for fn in cl_fns:
-                fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        sync_all()
-        cl_graphs, cl_keep = [], []
-        for fn in cl_fns:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cl_keep.append(fn())
-            cl_graphs.append(g)
-        n_cl = max(3, min(args.steps, 20))
-        acc = [0.0] * 4
-        for it in range(n_cl + 2):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            for j, g in enumerate(cl_graphs):
-                e[j].record()
-                g.replay()
-            e[4].record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                for j in range(4):
-                    acc[j] += e[j].elapsed_time(e[j + 1])
-        cl_ms = {n: acc[j] / n_cl for j, n in enumerate(names)}
-        del cl_graphs, cl_keep, gouts_cl
+            cl_fns += [op_fwd(p, True), op_bwd(p, go)]
+        warm(cl_fns, 2)
+        caps = [capture(fn) for fn in cl_fns]
+        cl_ms = dict(zip(names, time_graphs([c[0] for c in caps], n_it)))
+        del caps, gouts_cl
     except Exception as ex:      # reported, never fatal for the headline
         cl_ms = {"error": repr(ex)[:200]}
     sync_all()
@@ -329,35 +517,14 @@ def run_ours(args):
     #      (2 bytes per stored element); the tolerance of this path is stated in tests/test_gpu_parity.py ----
     bf16_ms = {}
     try:
-        if "bf16" in os.environ.get("CPM_BENCH_SKIP", ""):
+        if "bf16" in skip:
             raise RuntimeError("skipped")
         feats16 = [f.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
         b_fns = [(lambda p=p: pooler_forward(feats16, scales, rois, p, SAMPLING, False, 0, mapper)) for p in POOLERS]
-        with torch.cuda.stream(side):
-            for fn in b_fns:
-                fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        sync_all()
-        b_graphs, b_keep = [], []
-        for fn in b_fns:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                b_keep.append(fn())
-            b_graphs.append(g)
-        n_b = max(3, min(args.steps, 20))
-        acc = [0.0] * len(b_graphs)
-        for it in range(n_b + 2):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(len(b_graphs) + 1)]
-            for j, g in enumerate(b_graphs):
-                e[j].record()
-                g.replay()
-            e[len(b_graphs)].record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                for j in range(len(b_graphs)):
-                    acc[j] += e[j].elapsed_time(e[j + 1])
-        bf16_ms = {"fwd%d" % p[0]: acc[j] / n_b for j, p in enumerate(POOLERS)}
-        del b_graphs, b_keep, feats16
+        warm(b_fns, 2)
+        caps = [capture(fn) for fn in b_fns]
+        bf16_ms = dict(zip(["fwd%d" % p[0] for p in POOLERS], time_graphs([c[0] for c in caps], n_it)))
+        del caps, feats16
     except Exception as ex:
         bf16_ms = {"error": repr(ex)[:200]}
     sync_all()
@@ -365,48 +532,31 @@ def run_ours(args):
     # ---- the red.global.add fallback of the backward (non-deterministic order), reported separately ----
     atomic_ms = {}
     try:
-        at_fns = [(lambda p=p, go=go: pooler_backward(go, shapes, scales, rois, p, SAMPLING, False, 0, mapper, mode="atomic"))
-                  for p, go in zip(POOLERS, gouts)]
-        with torch.cuda.stream(side):
-            for fn in at_fns:
-                fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        sync_all()
-        at_graphs, at_keep = [], []
-        for fn in at_fns:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                at_keep.append(fn())
-            at_graphs.append(g)
-        acc = [0.0, 0.0]
-        for it in range(7):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            for j, g in enumerate(at_graphs):
-                e[j].record()
-                g.replay()
-            e[2].record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                acc[0] += e[0].elapsed_time(e[1])
-                acc[1] += e[1].elapsed_time(e[2])
-        atomic_ms = {"bwd7": acc[0] / 5, "bwd14": acc[1] / 5}
-        del at_graphs, at_keep
+        at_fns = [op_bwd(p, go, mode="atomic") for p, go in zip(POOLERS, gouts)]
+        warm(at_fns, 2)
+        caps = [capture(fn) for fn in at_fns]
+        atomic_ms = dict(zip(["bwd7", "bwd14"], time_graphs([c[0] for c in caps], 5)))
+        del caps
     except Exception as ex:
         atomic_ms = {"error": repr(ex)[:200]}
     sync_all()
 
+    # ---- the reference's own GPU RoIAlign on the same step (rank 0) ----
+    ref_gpu = reference_gpu_roi_align(feats_nchw, rois, gouts, scales) if rank == 0 and "refgpu" not in skip else {}
+    sync_all()
+
     # ---- e2e: host (pinned) buffers in and out, copies inside the timed region ----
-    # One step = H2D of the pyramid, the RoIs and both pooled gradients, the two Pooler modules forward + one autograd
+    # One step = H2D of the NCHW pyramid, the RoIs and both pooled gradients, the two Pooler modules forward + one autograd
     # backward (the feature gradient of both poolers accumulates into x.grad, as in the head), D2H of both pooled outputs
-    # and the gradient pyramid.  Three streams (H2D / compute / D2H) and two device input sets let step i+1's upload run
-    # under step i's compute and download (PCIe is full duplex); every step still moves all of its bytes.
-    def pinned(shape, channels_last=False):
-        return torch.empty(shape, pin_memory=True, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
-    feats_pin = [pinned(f.shape, True).copy_(f) for f in feats_h]
+    # and the NCHW gradient pyramid.  Three streams (H2D / compute / D2H) and two device input sets let step i+1's upload
+    # run under step i's compute and download (PCIe is full duplex); every step still moves all of its bytes.
+    def pinned(shape):
+        return torch.empty(shape, pin_memory=True)
+    feats_pin = [pinned(f.shape).copy_(f) for f in feats_h]
     rois_pin = pinned(rois_h.shape).copy_(rois_h)
     gouts_pin = [pinned(g.shape).copy_(g) for g in gouts_h]
     outs_pin = [pinned((K, CHANNELS, p[0], p[1])) for p in POOLERS]
-    grads_pin = [pinned(s, True) for s in shapes]
+    grads_pin = [pinned(s_) for s_ in shapes]
     assert all(t.is_pinned() for t in feats_pin + gouts_pin + outs_pin + grads_pin + [rois_pin])
     h2d = sum(t.numel() * 4 for t in feats_pin + gouts_pin) + rois_pin.numel() * 4
     d2h = sum(t.numel() * 4 for t in outs_pin + grads_pin)
@@ -422,13 +572,15 @@ def run_ours(args):
                               # their memory then returns to the allocator in stream order (no record_stream, whose
                               # deferred frees make the caching allocator fall back to cudaMalloc at unpredictable times)
 
-    def e2e_steps_run(n):
+    def e2e_steps_run(n, upload_pyramid=True, download_grads=True):
         for i in range(n):
             d = dev_sets[i & 1]
             with torch.cuda.stream(st_in):
                 st_in.wait_event(ev_c[i & 1])          # the compute that last read this input set has finished
-                for dst, src in zip(d["feats"] + d["gouts"] + [d["rois"]], feats_pin + gouts_pin + [rois_pin]):
-                    dst.copy_(src, non_blocking=True)
+                src = (feats_pin if upload_pyramid else []) + gouts_pin + [rois_pin]
+                dst = (d["feats"] if upload_pyramid else []) + d["gouts"] + [d["rois"]]
+                for dd, ss in zip(dst, src):
+                    dd.copy_(ss, non_blocking=True)
                 ev_in[i & 1].record(st_in)
             with torch.cuda.stream(st_c):
                 st_c.wait_event(ev_in[i & 1])
@@ -442,27 +594,61 @@ def run_ours(args):
                 ev_c[i & 1].record(st_c)
             with torch.cuda.stream(st_out):
                 st_out.wait_event(ev_c[i & 1])
-                res = [o.detach() for o in outs] + [x.grad for x in xs]
-                for dst, src in zip(outs_pin + grads_pin, res):
-                    dst.copy_(src, non_blocking=True)
+                res = [o.detach() for o in outs] + ([x.grad for x in xs] if download_grads else [])
+                for dd, ss in zip(outs_pin + grads_pin, res):
+                    dd.copy_(ss, non_blocking=True)
                 ev_out[i & 1].record(st_out)
             hold[i & 1] = (outs, xs, res, boxlists)
             del outs, xs, res, boxlists
         for s_ in (st_in, st_c, st_out):
             s_.synchronize()
 
-    e2e_steps = max(10, min(args.steps, 50))
-    e2e_steps_run(6)          # untimed: lets torch's caching allocator reach its steady state on all three streams
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_steps_run(e2e_steps)
-    sync_all()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    def e2e_measure(**kw):
+        n = max(10, min(args.steps, 50))
+        e2e_steps_run(6, **kw)    # untimed: lets torch's caching allocator reach its steady state on all three streams
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps_run(n, **kw)
+        sync_all()
+        ms = (time.perf_counter() - t0) * 1e3 / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n
+
+    e2e_ms, e2e_steps = e2e_measure()
     e2e_value = units_per_step / (e2e_ms * 1e-3)
+    # the case a head inside a resident model sees: the pyramid and its gradient stay on the device; per step the RoIs and
+    # the pooled gradients come from the host and the pooled outputs go back
+    res_ms, _ = e2e_measure(upload_pyramid=False, download_grads=False)
+    h2d_res = sum(t.numel() * 4 for t in gouts_pin) + rois_pin.numel() * 4
+    d2h_res = sum(t.numel() * 4 for t in outs_pin)
+    # bare copies of the same bytes, both directions at once: the PCIe / host-memory ceiling of this rank on this box
+    def bare_copies(n=6):
+        t0 = None
+        for i in range(n + 2):
+            if i == 2:
+                sync_all()
+                t0 = time.perf_counter()
+            with torch.cuda.stream(st_in):
+                for dd, ss in zip(dev_sets[0]["feats"] + dev_sets[0]["gouts"], feats_pin + gouts_pin):
+                    dd.copy_(ss, non_blocking=True)
+            with torch.cuda.stream(st_out):
+                for dd, ss in zip(outs_pin + grads_pin, keep_step[0:1] + keep_step[2:3] + keep_step[1] + keep_step[3]):
+                    dd.copy_(ss, non_blocking=True)
+        st_in.synchronize()
+        st_out.synchronize()
+        sync_all()
+        return (time.perf_counter() - t0) * 1e3 / n
+    try:
+        bare_ms = bare_copies()
+        if world > 1:
+            t = torch.tensor([bare_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bare_ms = float(t.item())
+    except Exception:
+        bare_ms = None
 
     # ---- NMS half of the metric (configs[2]) ----
     nms = bench_nms(ops, dev, rank, world, dist, sync_all)
@@ -471,43 +657,60 @@ def run_ours(args):
     det = bench_detect(ops, dev, rank)
     gtg = bench_grid_targets(ops, dev, rank)
     mat = bench_matcher(ops, dev, rank)
+    cfg0 = bench_config0(dev) if rank == 0 and "config0" not in skip else {}
 
     if rank == 0:
         peak, peak_src = measured_peak()
         ab = algorithmic_bytes(rois_h)
+        dram = ncu_dram_bytes()
         rl_ops = {n: {"ms": op_ms[n], "bytes": ab[n], "gbs": ab[n] / (op_ms[n] * 1e-3) / 1e9,
-                      "frac": ab[n] / (op_ms[n] * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": ab[n] / (op_ms[n] * 1e-3) / 1e9 / 8000.0}
+                      "frac": ab[n] / (op_ms[n] * 1e-3) / 1e9 / peak, "frac_of_nominal_8TBs": ab[n] / (op_ms[n] * 1e-3) / 1e9 / 8000.0,
+                      "traffic": dram.get(n)}
                   for n in names}
         top = max(names, key=lambda n: op_ms[n])
         total_bytes = sum(ab[n] for n in names)
-        # CPU baseline beside it: the full workload of the step (512 RoIs/img x 2 img), 4 passes (~10 s of CPU work)
+        resident_ms = sum(op_ms[n] for n in names)
+        # CPU baseline beside it: the full workload of the step (512 RoIs/img x 2 img), 4 passes (~18 s of CPU work)
         cpu_rate = cpu_dt = cpu_kind = cpu_sample = None
         if world == 1:
             runs = [cpu_reference_rate(ROIS_PER_IMG) for _ in range(4)]
             cpu_dt = sum(r[1] for r in runs)
             cpu_rate = sum(r[0] * r[1] for r in runs) / cpu_dt          # units / total seconds
             cpu_kind, cpu_sample = runs[0][2], runs[0][3] + ", 4 passes"
+        kernel_names = {"fwd7": "roi_align_fwd_cols<1> (7x7)", "fwd14": "roi_align_fwd_cols<2> (14x14)",
+                        "bwd7": "bwd_tiles_staged<0,7,2> (7x7) + bwd_prepare", "bwd14": "bwd_tiles_staged<0,14,2> (14x14) + bwd_prepare"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[1]: R-50-FPN CPM head RoIAlign 7x7 + 14x14 fwd+bwd, %d img/GPU, %d RoIs/img, "
                                        "4-level 256-ch fp32 pyramid of 800x1344 images, sampling_ratio 2" % (IMGS_PER_GPU, ROIS_PER_IMG),
-                           "layout": "pyramid channels_last (NHWC, zero-copy), pooled output (K,C,PH,PW) contiguous",
+                           "layout": "what the unmodified reference feeds and expects: NCHW-contiguous feature maps in (FPN.py:96-121), "
+                                     "pooled output (K,C,PH,PW), NCHW-contiguous feature gradients out; the NHWC staging of the "
+                                     "pyramid runs INSIDE the timed step, once per step (staging cache shared by the poolers)",
                            "backward": "deterministic tile-owner gather (no atomics)",
                            "unit_of_work": "one RoI through one pooler forward+backward; %d per step per GPU" % (K * len(POOLERS)),
-                           "launch": "each op captured once in a CUDA graph through the Python op layer and replayed; per-op time = CUDA "
-                                     "events between consecutive graph replays on the launching stream",
-                           "l2": "not flushed: per-step working set (pyramid 183 MB + pooled/grad_out 514 MB + gradients 366 MB) "
-                                 "exceeds the 126 MB L2",
-                           "parallelism": "dp%d (images sharded per GPU, no collective inside the ops)" % world},
-                "roofline": {"bound": "hbm", "kernel": {"fwd7": "roi_align_fwd_cols<1> (7x7)", "fwd14": "roi_align_fwd_cols<2> (14x14)",
-                                                         "bwd7": "bwd_tiles_staged<0,7,2> (7x7) + bwd_prepare",
-                                                         "bwd14": "bwd_tiles_staged<0,14,2> (14x14) + bwd_prepare"}[top],
+                           "launch": "the whole step captured once in a CUDA graph through the Python op layer and replayed; the "
+                                     "K-step region is timed with CUDA events on the launching stream, %d times, median reported "
+                                     "(all repeats in `repeats_ms`)" % n_rep,
+                           "l2": "not flushed: per-step working set (pyramid 183 MB + staged copy 183 MB + pooled/grad_out 514 MB + "
+                                 "gradients 366 MB) exceeds the 126 MB L2",
+                           "parallelism": "dp%d (images sharded per GPU, no collective inside the ops)" % world,
+                           "cpu_affinity": affinity},
+                "repeats_ms": [r * 1e3 for r in repeats],
+                "value_resident_channels_last": {"value": units_per_step / (resident_ms * 1e-3), "ms_per_step": resident_ms,
+                                                 "note": "the round-1 headline: the same four ops on a pyramid that is already "
+                                                         "channels_last (zero-copy NHWC) with channels_last-strided gradients, sum "
+                                                         "of the per-op graph times; comparable with BENCH_r01.value"},
+                "roofline": {"bound": "hbm", "kernel": kernel_names[top],
                              "achieved": rl_ops[top]["gbs"], "peak": peak, "unit": "GB/s", "frac": rl_ops[top]["frac"],
-                             "traffic": NCU_DRAM_BYTES.get(top), "traffic_source": NCU_DRAM_SOURCE, "peak_source": peak_src,
+                             "traffic": dram.get(top), "traffic_source": os.path.relpath(NCU_DRAM_FILE, ROOT) if dram else None,
+                             "peak_source": peak_src,
                              "step": {"bytes": total_bytes, "gbs": total_bytes / (ms_step * 1e-3) / 1e9,
-                                      "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak},
-                             "ops": rl_ops, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]},
+                                      "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                                      "note": "algorithmic bytes of the four ops (staging is overhead, SURVEY.md 8d) / the NCHW step"},
+                             "step_resident_channels_last": {"bytes": total_bytes, "gbs": total_bytes / (resident_ms * 1e-3) / 1e9,
+                                                             "frac": total_bytes / (resident_ms * 1e-3) / 1e9 / peak},
+                             "ops": rl_ops, "nchw_pieces_ms": nchw_ms, "U_px": {"7x7": ab["U7"], "14x14": ab["U14"]},
                              "backward_atomic_fallback_ms": atomic_ms,
                              "fwd_bf16_storage": ({n: {"ms": bf16_ms[n], "bytes": (ab[n] - 20 * K) // 2 + 20 * K,
                                                        "gbs": ((ab[n] - 20 * K) // 2 + 20 * K) / (bf16_ms[n] * 1e-3) / 1e9,
@@ -516,9 +719,21 @@ def run_ours(args):
                              "ops_channels_last_pooled": ({n: {"ms": cl_ms[n], "gbs": ab[n] / (cl_ms[n] * 1e-3) / 1e9,
                                                                "frac": ab[n] / (cl_ms[n] * 1e-3) / 1e9 / peak} for n in names}
                                                           if "error" not in cl_ms else cl_ms)},
+                "roi_align": {"reference_gpu": ref_gpu,
+                              "speedup_vs_reference_gpu": (ref_gpu["ms_per_step"] / ms_step if world == 1 and "ms_per_step" in ref_gpu
+                                                           else None)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms, "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn, "detection_postprocess": det, "grid_targets": gtg, "iou_matcher": mat}
+                        "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_ms * 1e-3) / 1e9,
+                        "bare_copies_ms": bare_ms,
+                        "note": "NCHW pyramid, RoIs and pooled gradients up, pooled outputs and NCHW gradient pyramid down, every "
+                                "step; bare_copies_ms = the same bytes with no kernels (this rank's PCIe / host-memory ceiling)",
+                        "pyramid_resident": {"value": units_per_step / (res_ms * 1e-3), "ms_per_step": res_ms,
+                                             "h2d_bytes_per_step": h2d_res, "d2h_bytes_per_step": d2h_res,
+                                             "note": "the case a head inside a resident model sees: pyramid and its gradient stay "
+                                                     "on the device; RoIs + pooled gradients up, pooled outputs down"}},
+                "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn,
+                "detection_postprocess": det, "grid_targets": gtg, "iou_matcher": mat, "config0": cfg0}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
@@ -534,7 +749,7 @@ def run_ours(args):
 def bench_nms(ops, dev, rank, world, dist, sync_all, iters=10):
     """configs[2]: batched NMS, 16 images: RPN flavour (5 levels x 1000 proposals, thr 0.7) and detection flavour
     (1000 proposals x 80 classes, score > 0.03 gate and un-gated stress, thr 0.3).  boxes/s = input boxes / time."""
-    from cpm_r_cnn_b200 import synthetic as sy
+    from cpm_r_cnn_b200 import _lib, synthetic as sy
     gen = torch.Generator().manual_seed(1000 + rank)
     res = {}
     cases = {}
@@ -563,10 +778,50 @@ def bench_nms(ops, dev, rank, world, dist, sync_all, iters=10):
         res[name] = {"boxes": int(b.shape[0]) * world, "segments": nseg * world, "ms": ms, "kept": int(total.item()),
                      "boxes_per_sec": b.shape[0] * world / (ms * 1e-3)}
         if rank == 0:
-            res[name]["reference_gpu"] = reference_gpu_nms(name, b, s, seg, nseg, thr, int(total.item()))
+            flavor = _lib.IOU_TV_CUDA if name.startswith("rpn") else _lib.IOU_ML_CUDA
+            ours_keep, ours_counts = ops.batched_nms(b, s, seg, nseg, thr, iou_flavor=flavor, return_counts=True)
+            res[name]["reference_gpu"] = reference_gpu_nms(name, b, s, seg, nseg, thr, ours_keep, ours_counts)
             if res[name]["reference_gpu"].get("ms"):
                 res[name]["speedup_vs_reference_gpu"] = res[name]["reference_gpu"]["ms"] * world / ms if world == 1 else None
+            res[name]["cpu_baseline"] = cpu_nms_baseline(name, b, s, seg, nseg, thr, ours_keep)
     return res
+
+
+def cpu_nms_baseline(name, b, s, seg, nseg, thr, ours_keep):
+    """The extension ships no CPU nms / ml_nms (ml_nms.h:38 "CPU version not implemented"), so -- as BASELINE.json's
+    north_star prescribes -- the equivalent torchvision.ops CPU op is timed on the host cores: one torchvision.ops.nms per
+    (image, level) segment for the RPN flavour, one torchvision.ops.batched_nms per image for the detection flavour."""
+    import torchvision
+    out = {}
+    try:
+        bc, sc, sg = b.cpu(), s.cpu(), seg.cpu().to(torch.int64)
+        order = torch.argsort(sg, stable=True)
+        counts = torch.bincount(sg, minlength=nseg).tolist()
+        bs, ss, gs = bc[order].contiguous(), sc[order].contiguous(), sg[order].contiguous()
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        kept, pos = [], 0
+        if name.startswith("rpn"):
+            for c in counts:
+                if c:
+                    kept.append(order[pos + torchvision.ops.nms(bs[pos:pos + c], ss[pos:pos + c], thr)])
+                pos += c
+            op = "torchvision.ops.nms (CPU) per (image, level)"
+        else:
+            n_cls = 80
+            for i in range(nseg // n_cls):
+                c = sum(counts[i * n_cls:(i + 1) * n_cls])
+                if c:
+                    kept.append(order[pos + torchvision.ops.batched_nms(bs[pos:pos + c], ss[pos:pos + c], gs[pos:pos + c], thr)])
+                pos += c
+            op = "torchvision.ops.batched_nms (CPU) per image"
+        dt = time.perf_counter() - t0
+        kept = torch.cat(kept) if kept else torch.empty(0, dtype=torch.int64)
+        out = {"op": op, "ms": dt * 1e3, "boxes_per_sec": b.shape[0] / dt, "cores": torch.get_num_threads(), "kind": "torchvision",
+               "same_keep_set_as_ours": bool(torch.equal(torch.sort(kept)[0], torch.sort(ours_keep.cpu())[0]))}
+    except Exception as e:
+        out = {"unavailable": repr(e)[:200]}
+    return out
 
 
 def bench_decode(ops, dev, rank, iters=20):
@@ -817,7 +1072,7 @@ def bench_matcher(ops, dev, rank, iters=20):
     return res
 
 
-def reference_gpu_nms(name, b, s, seg, nseg, thr, kept_ours):
+def reference_gpu_nms(name, b, s, seg, nseg, thr, ours_keep, ours_counts):
     """The reference's own single-GPU op path on the same boxes, timed with CUDA events in this process:
     RPN flavour  = one pet.lib.ops.nms (= torchvision.ops.nms, pet/lib/ops/nms.py:2,10) call per (image, level), the loop
                    of rpn/inference.py:102-113;
@@ -830,30 +1085,30 @@ def reference_gpu_nms(name, b, s, seg, nseg, thr, kept_ours):
         order = torch.argsort(seg.to(torch.int64), stable=True)
         counts = torch.bincount(seg.to(torch.int64), minlength=nseg).tolist()
         bs, ss = b[order].contiguous(), s[order].contiguous()
+        starts = [0]
+        for c in counts:
+            starts.append(starts[-1] + c)
         if name.startswith("rpn"):
-            chunks, pos = [], 0
-            for c in counts:
-                chunks.append((bs[pos:pos + c], ss[pos:pos + c]))
-                pos += c
-            fn = lambda: sum(int(torchvision.ops.nms(bb, sc, thr).numel()) for bb, sc in chunks if bb.shape[0])
+            chunks = [(bs[starts[i]:starts[i + 1]], ss[starts[i]:starts[i + 1]], starts[i]) for i in range(nseg) if counts[i]]
+            fn = lambda: [order[p0 + torchvision.ops.nms(bb, sc, thr)] for bb, sc, p0 in chunks]
             out["op"] = "torchvision.ops.nms per (image, level)"
         else:
             n_cls = 80
             labels = (seg.to(torch.int64) % n_cls + 1)[order].contiguous()
-            per_img, pos = [], 0
+            per_img = []
             for i in range(nseg // n_cls):
-                c = sum(counts[i * n_cls:(i + 1) * n_cls])
-                per_img.append((bs[pos:pos + c], ss[pos:pos + c], labels[pos:pos + c]))
-                pos += c
+                p0, p1 = starts[i * n_cls], starts[(i + 1) * n_cls]
+                if p1 > p0:
+                    per_img.append((bs[p0:p1], ss[p0:p1], labels[p0:p1], p0))
             try:
                 from oracle import build_ref
                 ref = build_ref.load("pet_ref_cuda")
-                fn = lambda: sum(int(ref.ml_nms(bb, sc, lb, thr, 0).numel()) for bb, sc, lb in per_img if bb.shape[0])
+                fn = lambda: [order[p0 + ref.ml_nms(bb, sc, lb, thr, 0)] for bb, sc, lb, p0 in per_img]
                 out["op"] = "_C.ml_nms (reference ml_nms.cu, unmodified) per image"
             except Exception:
-                fn = lambda: sum(int(torchvision.ops.batched_nms(bb, sc, lb, thr).numel()) for bb, sc, lb in per_img if bb.shape[0])
+                fn = lambda: [order[p0 + torchvision.ops.batched_nms(bb, sc, lb, thr)] for bb, sc, lb, p0 in per_img]
                 out["op"] = "torchvision.ops.batched_nms per image (reference build unavailable)"
-        kept = fn()
+        ref_keep = fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -862,7 +1117,18 @@ def reference_gpu_nms(name, b, s, seg, nseg, thr, kept_ours):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        out.update({"ms": ms, "boxes_per_sec": b.shape[0] / (ms * 1e-3), "kept": kept, "same_kept_count": kept == kept_ours})
+        # keep LISTS, not counts: per (image, level) segment in the reference's own order for the RPN flavour; per image as a
+        # set for the detection flavour (ml_nms orders an image's survivors by score over all classes, ours groups by class)
+        if name.startswith("rpn"):
+            same = bool(torch.equal(torch.cat(ref_keep), ours_keep))
+        else:
+            oc = torch.cumsum(ours_counts.reshape(-1, 80).sum(1), 0).tolist()
+            ours_img = [ours_keep[(oc[i - 1] if i else 0):oc[i]] for i in range(len(oc))]
+            ours_img = [k for k in ours_img if k.numel()]
+            same = len(ours_img) == len(ref_keep) and all(
+                torch.equal(torch.sort(a)[0], torch.sort(r)[0]) for a, r in zip(ours_img, ref_keep))
+        out.update({"ms": ms, "boxes_per_sec": b.shape[0] / (ms * 1e-3), "kept": int(sum(k.numel() for k in ref_keep)),
+                    "same_keep_lists": same})
     except Exception as e:
         out["unavailable"] = repr(e)[:200]
     return out

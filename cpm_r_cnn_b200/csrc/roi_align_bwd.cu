@@ -677,14 +677,19 @@ struct BwdWs {
 // the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
 static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
-// CPM_BWD_IMPL=tma selects the warp-specialised TMA tile kernel for the two CPM poolers (measured slower than the staged
-// kernel on the benchmark workload, DESIGN.md section 7: kept for A/B measurements); read once per process
-static bool tma_enabled() {
-  static const bool on = [] {
+// Which deterministic tile kernel takes a call (measured on the benchmark workload):
+//   NHWC gradient pyramid: the staged 8x8-tile kernel (7x7 0.131 ms, 14x14 0.231 ms; TMA kernel 0.137 / 0.360 ms)
+//   NCHW gradient pyramid: an 8-pixel-wide tile writes 32-byte pieces of the 128-byte lines of a channel plane (staged:
+//     0.182 / 0.280 ms); the TMA kernel's 8x32 tiles write whole lines (0.137 / 0.360 ms) -> it takes the 7x7 pooler.
+// CPM_BWD_IMPL=tma | staged forces one of them for A/B measurements; read once per process.
+static int bwd_impl_env() {
+  static const int v = [] {
     const char* e = getenv("CPM_BWD_IMPL");
-    return e != nullptr && strcmp(e, "tma") == 0;
+    if (e != nullptr && strcmp(e, "tma") == 0) return 1;
+    if (e != nullptr && strcmp(e, "staged") == 0) return 2;
+    return 0;
   }();
-  return on;
+  return v;
 }
 
 // tiles > 0: with the per-tile candidate lists of the TMA kernel
@@ -707,7 +712,10 @@ static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, long til
 }
 
 static bool tma_shape_ok(const cpm_pyramid_t* p, int PH, int PW, int G) {
-  return tma_enabled() && btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0;
+  if (!(btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0)) return false;
+  const int env = bwd_impl_env();
+  if (env != 0) return env == 1;
+  return p->layout == CPM_LAYOUT_NCHW && PH == 7;
 }
 
 extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,

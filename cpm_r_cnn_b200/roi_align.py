@@ -27,11 +27,51 @@ def _is_nhwc(t):
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
 
 
-def stage_nhwc(x):
-    """(B,C,H,W) any strides -> the same values as a channels_last tensor (zero-copy when it already is)."""
-    _lib.require_cuda(x, "input")
-    if _is_nhwc(x):
-        return x
+class _StagingCache(object):
+    """NHWC copies of NCHW feature maps, shared by the poolers of one iteration.
+
+    The reference's FPN emits NCHW maps (FPN.py:96-121) and a CPM iteration runs five Poolers over the same maps (box
+    head, three grid stages, re-score head): staging the pyramid once instead of once per Pooler removes ~366 MB of
+    traffic per extra call.  An entry is valid only for the very same tensor OBJECT (weak reference) at the same
+    in-place version, so a new iteration's maps -- even at the same address -- are never served a stale copy."""
+
+    def __init__(self, capacity=16):
+        self.capacity = capacity
+        self.entries = []                # (weakref to source, version, staged), most recent last
+        self.hits = self.misses = 0
+
+    def get(self, x):
+        import weakref
+        alive = []
+        found = None
+        for ref, ver, staged in self.entries:
+            src = ref()
+            if src is None:
+                continue
+            if src is x and ver == x._version and found is None:
+                found = staged
+            elif src is x:
+                continue                 # written in place since it was staged: drop
+            alive.append((ref, ver, staged))
+        self.entries = alive
+        if found is not None:
+            self.hits += 1
+            return found
+        self.misses += 1
+        staged = _stage_uncached(x)
+        self.entries.append((weakref.ref(x), x._version, staged))
+        if len(self.entries) > self.capacity:
+            self.entries = self.entries[-self.capacity:]
+        return staged
+
+    def clear(self):
+        self.entries = []
+
+
+STAGING_CACHE = _StagingCache()
+
+
+def _stage_uncached(x):
     if x.dtype not in _lib.DTYPES:
         return x.contiguous(memory_format=torch.channels_last)
     src = x.contiguous()
@@ -41,6 +81,17 @@ def stage_nhwc(x):
         _lib.check(_lib.lib().cpm_layout_convert(_lib.ptr(src), _lib.ptr(dst), B, C, H, W, _lib.DTYPES[x.dtype],
                                                  _lib.NHWC, _lib.stream_ptr(x.device)))
     return dst
+
+
+def stage_nhwc(x, cache=True):
+    """(B,C,H,W) any strides -> the same values as a channels_last tensor (zero-copy when it already is; otherwise one
+    streaming transpose, remembered for the other poolers that read the same tensor in this iteration)."""
+    _lib.require_cuda(x, "input")
+    if _is_nhwc(x):
+        return x
+    if cache:
+        return STAGING_CACHE.get(x)
+    return _stage_uncached(x)
 
 
 def make_pyramid(levels, scales, layout):

@@ -943,3 +943,95 @@ def test_iou_and_matcher_random_vs_oracle():
         assert np.array_equal(q.cpu().numpy(), ref)
         for hi, lo, allow in ((0.7, 0.3, True), (0.5, 0.5, False), (0.5, 0.1, True)):
             assert np.array_equal(ops.Matcher(hi, lo, allow)(q).cpu().numpy(), om.match(ref, hi, lo, allow))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parity at the benchmark's own shape (bench.make_workload(0): 800x1344 images, P2 = 200x336, K = 1024, C = 256)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P", [7, 14])
+def test_bench_workload_parity(P):
+    """The exact tensors bench.py times -- NCHW maps in (staged inside the op), both poolers, forward + deterministic
+    backward writing NCHW -- against the reference's own CUDA kernels live (all channels) and, on a channel subsample,
+    under the |ref_cpu - ref_cuda| + 1e-5 bound of test_live_reference_cuda_roi_align with the scalar oracle as ref_cpu."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    ref = _ref_cuda()
+    rois_h, feats_h, gouts_h = bench.make_workload(0)
+    B, C = feats_h[0].shape[0], feats_h[0].shape[1]
+    go_h = gouts_h[0] if P == 7 else gouts_h[1]
+    m = _lib.make_mapper(2, 5)
+    rois = rois_h.cuda()
+    xs = [f.cuda() for f in feats_h]                                    # NCHW-contiguous, as the reference's FPN emits them
+    shapes = [tuple(f.shape) for f in feats_h]
+    out = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m)
+    go = go_h.cuda()
+    grads = pooler_backward(go, shapes, SCALES, rois, (P, P), 2, False, 0, m, mode="deterministic", nchw_grad=True)
+    grads2 = pooler_backward(go, shapes, SCALES, rois, (P, P), 2, False, 0, m, mode="deterministic", nchw_grad=False)
+    assert all(g.is_contiguous() for g in grads)
+    for a, b in zip(grads, grads2):
+        assert torch.equal(a, b)                                       # NCHW and NHWC write-outs: the same values
+    levels = oracle.level_map(rois_h.numpy(), 2, 5)
+    assert np.array_equal(levels, synthetic.fpn_levels_host(rois_h).numpy())
+    ch = np.arange(0, C, 8)                                            # channels the scalar oracle restates (every lane group)
+    cht = torch.as_tensor(ch).cuda()
+    CS = len(ch)
+    for l in range(4):
+        sel = levels == l
+        idx = torch.as_tensor(np.nonzero(sel)[0]).cuda()
+        r = rois[idx].contiguous()
+        _, _, H, W = shapes[l]
+        ro = ref.roi_align_forward(xs[l], r, SCALES[l], P, P, 2, False, 0)
+        mine = out[idx]
+        rms = float(ro.pow(2).mean().sqrt())
+        # all 256 channels: gross-error detector only (the reference's CUDA and CPU builds differ from each other by a few
+        # 1e-5 at these coordinates, see test_live_reference_cuda_roi_align); the exact bound follows on the subsample
+        assert bool(((mine - ro).abs() <= 5e-4 * (ro.abs() + rms)).all())
+        cpu = oracle.roi_align_forward(feats_h[l][:, ch].contiguous().numpy(), rois_h.numpy()[sel], SCALES[l], P, P, 2, False)
+        ro_s = ro[:, cht].cpu().numpy().astype(np.float64)
+        mine_s = mine[:, cht].cpu().numpy().astype(np.float64)
+        assert np.all(np.abs(mine_s - ro_s) <= np.abs(cpu - ro_s) + 1e-5 * (np.abs(ro_s) + rms))
+        close(mine_s, cpu)
+        rg = ref.roi_align_backward(go[idx].contiguous(), r, SCALES[l], P, P, B, C, H, W, 2, False, 0)
+        gabs = ref.roi_align_backward(go[idx].abs().contiguous(), r, SCALES[l], P, P, B, C, H, W, 2, False, 0)
+        grms = float(rg.pow(2).mean().sqrt())
+        assert bool(((grads[l] - rg).abs() <= 5e-4 * (gabs + grms)).all())          # all channels, gross errors only
+        gcpu = oracle.roi_align_backward(go_h[sel][:, ch].contiguous().numpy(), rois_h.numpy()[sel], SCALES[l], P, P, B, CS,
+                                         H, W, 2, False)
+        gm = grads[l][:, cht].cpu().numpy().astype(np.float64)
+        rg_s, gabs_s = rg[:, cht].cpu().numpy().astype(np.float64), gabs[:, cht].cpu().numpy().astype(np.float64)
+        assert np.all(np.abs(gm - rg_s) <= np.abs(gcpu - rg_s) + 1e-5 * (gabs_s + grms))
+        close_sum(gm, gcpu, gabs_s)
+
+
+def test_staging_cache_is_per_tensor_object():
+    """NCHW maps are staged once per tensor object and in-place version: a second pooler reuses the copy, a new tensor at
+    the same address or an in-place write does not."""
+    import importlib
+    ra = importlib.import_module("cpm_r_cnn_b200.roi_align")
+    ra.STAGING_CACHE.clear()
+    x = torch.randn(2, 64, 20, 30, device="cuda")
+    a = ra.stage_nhwc(x)
+    assert ra.stage_nhwc(x) is a and torch.equal(a, x) and a.is_contiguous(memory_format=torch.channels_last)
+    x.add_(1.0)
+    b = ra.stage_nhwc(x)
+    assert b is not a and torch.equal(b, x)
+    ptr = x.data_ptr()
+    del x, a, b
+    y = torch.randn(2, 64, 20, 30, device="cuda")                      # usually lands on the freed block
+    c = ra.stage_nhwc(y)
+    assert torch.equal(c, y), "stale staging copy served for a new tensor (same address: %s)" % (y.data_ptr() == ptr)
+
+
+def test_tma_backward_kernel_selfcheck():
+    """The opt-in TMA tile kernel (CPM_BWD_IMPL=tma; the switch is read once per process, hence the subprocess): NHWC and
+    NCHW gradients of both CPM poolers on the bench workload against the red.global.add scatter, run-to-run bit identity."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CPM_BWD_IMPL="tma")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bwd_check.py")], capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0 and "BWD_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
