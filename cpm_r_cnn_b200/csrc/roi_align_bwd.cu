@@ -623,6 +623,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
       float* dst = (float*)pv.ptr[l] + (((long)b * C + c0 + 4 * lane) * H + y) * W + x0;
       const long cs = (long)H * W;
       const bool v4 = (W & 3) == 0 && x0 + TW <= W;
+      const bool v8 = (W & 7) == 0 && x0 + TW <= W;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         float v[TW];
@@ -633,7 +634,9 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
           v[x] = (j & 1) ? hi : lo;
         }
         float* row = dst + j * cs;
-        if (v4) {
+        if (v8) {
+          st_global_v8(row, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        } else if (v4) {
           reinterpret_cast<float4*>(row)[0] = make_float4(v[0], v[1], v[2], v[3]);
           reinterpret_cast<float4*>(row)[1] = make_float4(v[4], v[5], v[6], v[7]);
         } else {
@@ -677,11 +680,10 @@ struct BwdWs {
 // the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
 static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
-// Which deterministic tile kernel takes a call (measured on the benchmark workload):
-//   NHWC gradient pyramid: the staged 8x8-tile kernel (7x7 0.131 ms, 14x14 0.231 ms; TMA kernel 0.137 / 0.360 ms)
-//   NCHW gradient pyramid: an 8-pixel-wide tile writes 32-byte pieces of the 128-byte lines of a channel plane (staged:
-//     0.182 / 0.280 ms); the TMA kernel's 8x32 tiles write whole lines (0.137 / 0.360 ms) -> it takes the 7x7 pooler.
-// CPM_BWD_IMPL=tma | staged forces one of them for A/B measurements; read once per process.
+// Which deterministic tile kernel takes a call (measured on the benchmark workload): the staged
+// 8x8-tile kernel -- NHWC pyramid 7x7 0.135 ms / 14x14 0.231 ms, NCHW pyramid 0.152 / 0.252 ms; the TMA tile kernel
+// measures 0.139 / 0.362 ms (NHWC) and 0.152 / 0.385 ms (NCHW).  CPM_BWD_IMPL=tma selects the latter for the two CPM
+// poolers (A/B measurements); read once per process.
 static int bwd_impl_env() {
   static const int v = [] {
     const char* e = getenv("CPM_BWD_IMPL");
@@ -713,9 +715,7 @@ static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, long til
 
 static bool tma_shape_ok(const cpm_pyramid_t* p, int PH, int PW, int G) {
   if (!(btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0)) return false;
-  const int env = bwd_impl_env();
-  if (env != 0) return env == 1;
-  return p->layout == CPM_LAYOUT_NCHW && PH == 7;
+  return bwd_impl_env() == 1;
 }
 
 extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,

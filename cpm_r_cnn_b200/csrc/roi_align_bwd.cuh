@@ -21,6 +21,13 @@ __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
+// one full 32-byte sector per lane and instruction (STG.256, sm_100): what an NCHW write-out of 8 consecutive columns wants
+__device__ __forceinline__ void st_global_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f),
+               "f"(g), "f"(h)
+               : "memory");
+}
+
 // One sample coordinate of one RoI along one axis (bilinear_interpolate_gradient, ROIAlign_cuda.cu:113-171, per axis).
 struct __align__(16) TapS {
   int lo, hi;       // lo < 0: sample out of range

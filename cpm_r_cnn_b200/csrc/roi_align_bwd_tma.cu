@@ -390,11 +390,17 @@ bwd_tiles_tma(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ C
   if (NCHW_OUT) {
     float* dst = (float*)pv.ptr[id.l] + (((long)id.b * C + c) * H + y0) * W + xg;
     const bool v4 = (W & 3) == 0 && xg + 8 <= W;
+    const bool v8 = (W & 7) == 0 && xg + 8 <= W;
 #pragma unroll
     for (int y = 0; y < TH; y++) {
       if (y0 + y >= H) break;
       float* row = dst + (long)y * W;
-      if (v4) {
+      if (v8) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) unpack2(acc[y][j], a[2 * j], a[2 * j + 1]);
+        st_global_v8(row, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+      } else if (v4) {
         reinterpret_cast<ulonglong2*>(row)[0] = make_ulonglong2(acc[y][0], acc[y][1]);
         reinterpret_cast<ulonglong2*>(row)[1] = make_ulonglong2(acc[y][2], acc[y][3]);
       } else {
