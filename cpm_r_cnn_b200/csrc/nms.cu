@@ -60,12 +60,18 @@ __device__ __forceinline__ unsigned desc_key(float s) {
   return ~u;
 }
 
+// trash >= 0: segment ids outside [0, trash) -- negative ones included -- are redirected to segment `trash`, which the sweep
+// drops as a whole (a stray id can then neither write seg_counts out of bounds nor split a real segment)
 template <typename SegT>
-__global__ void nms_build_keys(const float* __restrict__ scores, const SegT* __restrict__ segs, int N,
+__global__ void nms_build_keys(const float* __restrict__ scores, const SegT* __restrict__ segs, int N, long long trash,
                                unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const unsigned long long seg = segs ? (unsigned long long)(unsigned)segs[i] : 0ull;
+  unsigned long long seg = 0ull;
+  if (segs) {
+    const long long v = (long long)segs[i];
+    seg = (trash >= 0 && (v < 0 || v >= trash)) ? (unsigned long long)trash : (unsigned long long)(unsigned)v;
+  }
   keys[i] = (seg << 32) | desc_key(scores[i]);
   vals[i] = i;
 }
@@ -93,9 +99,9 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
                                                             long long topk, int flavor, unsigned char* __restrict__ flags,
                                                             long long* __restrict__ seg_counts,
                                                             unsigned long long* __restrict__ total_kept,
-                                                            int* __restrict__ d_error) {
+                                                            unsigned* __restrict__ rem_g, long long trash) {
   __shared__ float4 sb[kSweepCap];
-  __shared__ unsigned rem[kSweepMaxSeg / 32];
+  __shared__ unsigned rem_s[kSweepMaxSeg / 32];
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_kept;
   __shared__ int s_done;
@@ -106,8 +112,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
     const int beg = starts[s];
     const int end = s + 1 < nseg ? starts[s + 1] : N;
     const int n = end - beg;
-    if (n > kSweepMaxSeg) {               // documented limit of this kernel
-      if (tid == 0) *d_error = 1;
+    if (trash >= 0 && (long long)(keys[beg] >> 32) >= trash) {      // boxes with an out-of-range segment id: all dropped
       for (int j = tid; j < n; j += kSweepThreads) flags[beg + j] = 0;
       continue;
     }
@@ -115,6 +120,11 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
     const float4* gb = sboxes + beg;
     if (in_smem)
       for (int j = tid; j < n; j += kSweepThreads) sb[j] = gb[j];
+    // suppression bits: shared memory up to 65 536 boxes, a private slice of the workspace beyond (two big segments start
+    // more than 65 536 boxes apart, so beg / 32 + 2 * (beg / 65536) never lets their word ranges touch)
+    const bool big = n > kSweepMaxSeg;
+    unsigned* const remg = rem_g + (beg >> 5) + 2 * (beg >> 16);
+    auto sweep_segment = [&](unsigned* rem) {
     for (int j = tid; j < (n + 31) / 32; j += kSweepThreads) rem[j] = 0u;
     __syncthreads();
     long long kept_total = 0;
@@ -213,6 +223,9 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
       if (total_kept) atomicAdd(total_kept, (unsigned long long)kept_total);
     }
     __syncthreads();
+    };
+    if (big) sweep_segment(remg);
+    else sweep_segment(rem_s);
   }
 }
 
@@ -239,7 +252,7 @@ struct ToI64 {
 
 // ---- workspace carving ----
 struct NmsWs {
-  size_t keys_a, keys_b, vals_a, vals_b, sboxes, flags, heads, starts, scalars, cub, total;
+  size_t keys_a, keys_b, vals_a, vals_b, sboxes, flags, heads, starts, scalars, rem, cub, total;
   size_t cub_bytes;
 };
 
@@ -259,6 +272,7 @@ static NmsWs nms_layout(int64_t N) {
   w.heads = take(n);
   w.starts = take((n + 1) * 4);
   w.scalars = take(64);
+  w.rem = take((n / 32 + 2 * (n / 65536) + 8) * 4);     // suppression bits of segments above 65 536 boxes
   // cub temp storage: asked from cub when a device is present, else a documented upper bound
   size_t t1 = 0, t2 = 0, t3 = 0;
   cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, t1, (const unsigned long long*)nullptr,
@@ -322,7 +336,7 @@ static int run_nms(const float* d_boxes, const float* d_scores, const void* d_se
   unsigned char* heads = (unsigned char*)(base + w.heads);
   int* starts = (int*)(base + w.starts);
   int* d_nseg = (int*)(base + w.scalars);
-  int* d_err = d_nseg + 1;
+  unsigned* rem_g = (unsigned*)(base + w.rem);
   unsigned long long* d_total = (unsigned long long*)(base + w.scalars + 16);
   void* cub_tmp = base + w.cub;
   size_t cub_bytes = w.cub_bytes;
@@ -330,12 +344,13 @@ static int run_nms(const float* d_boxes, const float* d_scores, const void* d_se
   const int n = (int)N;
   const int tb = 256, gb = (n + tb - 1) / tb;
   CPM_CHECK_CUDA(cudaMemsetAsync(base + w.scalars, 0, 64, st));
+  const long long trash = mode == 1 ? (long long)num_segments : -1LL;
   if (mode == 2)
-    nms_build_keys<long long><<<gb, tb, 0, st>>>(d_scores, (const long long*)d_segs, n, keys_a, vals_a);
+    nms_build_keys<long long><<<gb, tb, 0, st>>>(d_scores, (const long long*)d_segs, n, -1LL, keys_a, vals_a);
   else
-    nms_build_keys<int><<<gb, tb, 0, st>>>(d_scores, mode == 1 ? (const int*)d_segs : nullptr, n, keys_a, vals_a);
+    nms_build_keys<int><<<gb, tb, 0, st>>>(d_scores, mode == 1 ? (const int*)d_segs : nullptr, n, trash, keys_a, vals_a);
   CPM_CHECK_LAUNCH();
-  const int end_bit = mode == 0 ? 32 : (mode == 1 ? 32 + bits_for(num_segments) : 64);
+  const int end_bit = mode == 0 ? 32 : (mode == 1 ? 32 + bits_for(num_segments + 1) : 64);
   CPM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, vals_a, vals_b, n, 0, end_bit, st));
   count_launch(3);
   nms_gather<<<gb, tb, 0, st>>>(d_boxes, keys_b, vals_b, n, sboxes, heads);
@@ -349,10 +364,10 @@ static int run_nms(const float* d_boxes, const float* d_scores, const void* d_se
   if (wide)
     nms_sweep<true><<<mode == 0 ? 1 : 148 * 2, 1024, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr,
                                                               mode == 2 ? 0LL : (long long)topk, flavor, flags,
-                                                              mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, d_err);
+                                                              mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, rem_g, trash);
   else
     nms_sweep<false><<<148 * 4, 256, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, mode == 2 ? 0LL : (long long)topk,
-                                              flavor, flags, mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, d_err);
+                                              flavor, flags, mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, rem_g, trash);
   CPM_CHECK_LAUNCH();
   if (mode == 2) {
     nms_rekey<<<gb, tb, 0, st>>>(keys_b, vals_b, flags, n, keys_a);

@@ -834,7 +834,21 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     CPM_CHECK_ARG(tiles * chunks < (1L << 31), "gradient pyramid too large for one launch");
     const bst::StagedFn fn = pooled_layout == CPM_POOLED_KHWC ? bst::pick_staged<true>(pooled_h, pooled_w, sampling_ratio)
                                                               : bst::pick_staged<false>(pooled_h, pooled_w, sampling_ratio);
-    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
+    {
+      // opt-in to the dynamic shared memory, once per (instantiation, device, host thread)
+      static thread_local const void* done_fn[8];
+      static thread_local int done_dev[8], ndone = 0;
+      int dev, hit = 0;
+      CPM_CHECK_CUDA(cudaGetDevice(&dev));
+      for (int i = 0; i < ndone; i++) hit |= done_fn[i] == (const void*)fn && done_dev[i] == dev;
+      if (!hit) {
+        CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bst::Smem)));
+        if (ndone < 8) {
+          done_fn[ndone] = (const void*)fn;
+          done_dev[ndone++] = dev;
+        }
+      }
+    }
     fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
         pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
     CPM_CHECK_LAUNCH();

@@ -586,11 +586,27 @@ bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
   return true;
 }
 
-// channel chunks pooled by one CTA (must divide the chunk count)
+// channel chunks pooled by one CTA (must divide the chunk count); CPM_FWD_CPC overrides it (A/B measurements; read once)
 static int chunks_per_cta(int chunks, int want) {
-  if (const char* e = getenv("CPM_FWD_CPC")) want = atoi(e) > 0 ? atoi(e) : want;
+  static const int forced = [] {
+    const char* e = getenv("CPM_FWD_CPC");
+    return e != nullptr && atoi(e) > 0 ? atoi(e) : 0;
+  }();
+  if (forced > 0) want = forced;
   while (want > 1 && chunks % want != 0) want--;
   return want < 1 ? 1 : want;
+}
+
+// opt-in to the dynamic shared memory of one instantiation, once per device and host thread
+template <typename F>
+static int configure_once(F fn, size_t smem, int& configured_dev) {
+  int dev;
+  CPM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_dev = dev;
+  }
+  return CPM_OK;
 }
 
 template <bool BF>
@@ -605,14 +621,16 @@ static int launch_fwd_cols_t(const PyramidView& pv, const float* rois, long K, i
     const int chunks = pv.channels / 128;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
     auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<1, true, BF> : fwdc::roi_align_fwd_cols<1, false, BF>;
-    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    static thread_local int cfg[2] = {-1, -1};
+    if (int rc = configure_once(fn, smem1, cfg[out_channels_last ? 1 : 0])) return rc;
     const int cpc = chunks_per_cta(chunks, 1);
     fn<<<(unsigned)(K * (chunks / cpc)), 224, smem1, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   } else {
     const int chunks = pv.channels / 64;
     CPM_CHECK_ARG(K * chunks < (1L << 31), "too many RoIs for one launch");
     auto fn = out_channels_last ? fwdc::roi_align_fwd_cols<2, true, BF> : fwdc::roi_align_fwd_cols<2, false, BF>;
-    CPM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    static thread_local int cfg[2] = {-1, -1};
+    if (int rc = configure_once(fn, smem2, cfg[out_channels_last ? 1 : 0])) return rc;
     const int cpc = chunks_per_cta(chunks, 2);
     fn<<<(unsigned)(K * (chunks / cpc)), 448, smem2, st>>>(pv, rois, G, aligned, mp, lv, out, chunks, cpc);
   }

@@ -113,10 +113,12 @@ class Pooler(nn.Module):
             self.poolers[0].pooled_memory_format = self.pooled_memory_format
             self.poolers[0].native_bf16 = self.native_bf16
             return self.poolers[0](x[0], rois)
+        result_dtype = x[0].dtype             # poolers.py:119-131: the result is allocated in, and cast back to, x[0].dtype
         levels = [_float_function(t, self.native_bf16) for t in list(x)[:num_levels]]
         rois = _float_function(rois)
         rois = rois.to(torch.float32 if levels[0].dtype == torch.bfloat16 else levels[0].dtype)
         cfg = (self.output_size, self.scales[:len(levels)], self.sampling_ratio, self.aligned,
                INTERPOLATION_METHOD[self.interpolation], self.map_levels.c_struct(),
                self.pooled_memory_format == torch.channels_last)
-        return _PyramidROIAlign.apply(rois, cfg, *levels)
+        out = _PyramidROIAlign.apply(rois, cfg, *levels)
+        return out if out.dtype == result_dtype else out.to(result_dtype)

@@ -229,12 +229,12 @@ def pooler_backward(grad_output, shapes, scales, rois, output_size, sampling_rat
 
 
 class _ROIAlign(Function):
-    """pet/lib/ops/roi_align.py:14-60 (same argument list, same `(grad_input, None x 6)` backward)."""
-
-    pooled_channels_last = False     # set by ROIAlign.forward around the call (the Function keeps the reference signature)
+    """pet/lib/ops/roi_align.py:14-60: the reference's argument list and its `(grad_input, None x 6)` backward, plus one
+    optional trailing argument (extension): channels_last=True returns the pooled tensor with channels_last strides."""
 
     @staticmethod
-    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio, aligned, interpolation="bilinear"):
+    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio, aligned, interpolation="bilinear",
+                channels_last=False):
         ctx.save_for_backward(roi)
         ctx.output_size = _pair(output_size)
         ctx.spatial_scale = spatial_scale
@@ -244,7 +244,7 @@ class _ROIAlign(Function):
         ctx.interpolation_method = INTERPOLATION_METHOD[interpolation]
         ctx.nchw_input = not _is_nhwc(input)
         return pooler_forward([input], [spatial_scale], roi, ctx.output_size, sampling_ratio, aligned,
-                              ctx.interpolation_method, None, channels_last=_ROIAlign.pooled_channels_last)
+                              ctx.interpolation_method, None, channels_last=bool(channels_last))
 
     @staticmethod
     @once_differentiable
@@ -253,7 +253,7 @@ class _ROIAlign(Function):
         grad_input = pooler_backward(grad_output, [ctx.input_shape], [ctx.spatial_scale], rois, ctx.output_size,
                                      ctx.sampling_ratio, ctx.aligned, ctx.interpolation_method, None,
                                      nchw_grad=ctx.nchw_input)[0]
-        return grad_input, None, None, None, None, None, None
+        return grad_input, None, None, None, None, None, None, None
 
 
 roi_align = _ROIAlign.apply
@@ -289,12 +289,9 @@ class ROIAlign(nn.Module):
     def forward(self, input, rois):
         """input: NCHW images (any strides); rois: Bx5 boxes, first column = index into N, then xyxy."""
         assert rois.dim() == 2 and rois.size(1) == 5
-        _ROIAlign.pooled_channels_last = self.pooled_memory_format == torch.channels_last
-        try:
-            return roi_align(_float_function(input, self.native_bf16), _float_function(rois), self.output_size,
-                             self.spatial_scale, self.sampling_ratio, self.aligned, self.interpolation_method)
-        finally:
-            _ROIAlign.pooled_channels_last = False
+        return roi_align(_float_function(input, self.native_bf16), _float_function(rois), self.output_size,
+                         self.spatial_scale, self.sampling_ratio, self.aligned, self.interpolation_method,
+                         self.pooled_memory_format == torch.channels_last)
 
     def __repr__(self):
         tmpstr = self.__class__.__name__ + "("

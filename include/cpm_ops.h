@@ -63,8 +63,7 @@ extern "C" {
 /* forward implementation selector (testing / benchmarking aid; AUTO is what callers use) */
 #define CPM_FWD_AUTO 0
 #define CPM_FWD_GENERIC 1         /* one thread per output element, any parameters / layout, fp32/fp64 */
-#define CPM_FWD_NHWC 2            /* warp-per-bin-row channel-vector gather (bilinear, NHWC, fp32, C % 4 == 0) */
-#define CPM_FWD_NHWC_ROWS 3       /* the earlier register-row variant of CPM_FWD_NHWC (kept for A/B measurements) */
+#define CPM_FWD_NHWC 2            /* general channel-vector gather (bilinear, NHWC, fp32, C % 4 == 0, any pooled size) */
 #define CPM_FWD_COLS 4            /* column-table kernel: 7x7 / 14x14 poolers, sampling_ratio 1|2, NHWC fp32 (AUTO's choice) */
 
 /*
@@ -115,7 +114,7 @@ CPM_API int cpm_set_device(int device);
  * (K, C, PH, PW) -- one launch, no nonzero()/index_put, no device sync.
  *   d_rois      (K,5) [batch_idx, x1, y1, x2, y2], same dtype as the pyramid (ROIAlign_cuda.cu:381-382)
  *   mapper      ignored when num_levels == 1; d_roi_levels (optional, int32[K]) overrides the mapper
- *   impl        CPM_FWD_AUTO | CPM_FWD_GENERIC | CPM_FWD_NHWC | CPM_FWD_NHWC_ROWS | CPM_FWD_COLS
+ *   impl        CPM_FWD_AUTO | CPM_FWD_GENERIC | CPM_FWD_NHWC | CPM_FWD_COLS
  * K == 0 is a no-op (ROIAlign_cuda.cu:401-404). */
 CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
                           int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,

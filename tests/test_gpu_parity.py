@@ -658,7 +658,10 @@ def test_roi_align_native_bf16(pooled, sr):
     pooler = ops.Pooler("ROIAlign", pooled, SCALES, sr)
     boxlists = [ops.BoxList(rois[rois[:, 0] == i][:, 1:], (336, 200)) for i in range(B)]
     xg = [x.detach().requires_grad_(True) for x in xb]
-    assert pooler(xg, boxlists).dtype == torch.float32          # default = the reference's cast (apex float_function)
+    # default = the reference: computed in fp32 (apex float_function), returned in x[0].dtype (poolers.py:119-131)
+    y32 = pooler(xg, boxlists)
+    rois_b = pooler.convert_to_roi_format(boxlists)              # the module pools image by image
+    assert y32.dtype == torch.bfloat16 and torch.equal(y32, pooler_forward(xf, SCALES, rois_b, pooled, sr, False, 0, m).to(torch.bfloat16))
     pooler.native_bf16 = True
     y = pooler(xg, boxlists)
     assert y.dtype == torch.bfloat16
@@ -1035,3 +1038,57 @@ def test_tma_backward_kernel_selfcheck():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "bwd_check.py")], capture_output=True, text=True, env=env,
                        timeout=600)
     assert r.returncode == 0 and "BWD_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# robustness items (round-1 review)
+# ----------------------------------------------------------------------------------------------------------------
+def test_nms_segment_above_65536_boxes():
+    """One segment larger than the shared-memory suppression bitmap (65 536 boxes): the bits move to the workspace, the
+    keep list still equals torchvision's CUDA nms bit for bit."""
+    import torchvision
+    gen = torch.Generator().manual_seed(70)
+    n = 70000
+    boxes = synthetic.coco_like_boxes(gen, n).cuda()
+    scores = synthetic.tie_free_scores(gen, n).cuda()
+    got = ops.nms(boxes, scores, 0.5)
+    want = torchvision.ops.nms(boxes, scores, 0.5)
+    assert torch.equal(got, want)
+    seg = torch.zeros(n, dtype=torch.int32, device="cuda")
+    seg[n // 2:] = 1
+    keep, counts = ops.batched_nms(boxes, scores, seg, 2, 0.5, return_counts=True)
+    w0 = torchvision.ops.nms(boxes[:n // 2], scores[:n // 2], 0.5)
+    w1 = torchvision.ops.nms(boxes[n // 2:], scores[n // 2:], 0.5) + n // 2
+    assert torch.equal(keep, torch.cat([w0, w1])) and counts.tolist() == [w0.numel(), w1.numel()]
+
+
+def test_batched_nms_out_of_range_segment_ids_are_dropped():
+    """Segment ids outside [0, num_segments) -- negative ones included -- neither corrupt the counts nor survive."""
+    gen = torch.Generator().manual_seed(71)
+    b, s, seg = synthetic.rpn_like_candidates(gen, 1, 3, 200)
+    bad = seg.clone()
+    bad[::7] = -1
+    bad[3::11] = 3
+    bad[5::13] = 1 << 20
+    ok = (bad >= 0) & (bad < 3)
+    keep, counts = ops.batched_nms(b.cuda(), s.cuda(), bad.cuda(), 3, 0.7, return_counts=True)
+    idx = torch.nonzero(ok).squeeze(1)
+    keep2, counts2 = ops.batched_nms(b[idx].cuda(), s[idx].cuda(), bad[idx].cuda(), 3, 0.7, return_counts=True)
+    assert torch.equal(keep.cpu(), idx[keep2.cpu()]) and torch.equal(counts, counts2)
+
+
+def test_bad_image_index_gives_zeros_on_every_forward_path():
+    x = torch.randn(2, 8, 20, 30, generator=torch.Generator().manual_seed(3)).cuda()
+    rois = torch.tensor([[0, 2, 2, 20, 15], [5, 2, 2, 20, 15], [-1, 2, 2, 20, 15]], dtype=torch.float32).cuda()
+    for impl, xx in ((_lib.FWD_GENERIC, x), (_lib.FWD_NHWC, x.contiguous(memory_format=torch.channels_last))):
+        out = pooler_forward([xx], [0.25], rois, (5, 3), 2, False, 0, None, impl=impl)
+        assert float(out[0].abs().max()) > 0 and float(out[1:].abs().max()) == 0.0
+
+
+def test_multilevel_pooler_returns_the_input_dtype():
+    """poolers.py:119-131 allocates the result in x[0].dtype and casts every level's output back to it."""
+    gen = torch.Generator().manual_seed(9)
+    feats = [f.cuda().half() for f in synthetic.pyramid(gen, 1, 16, 64, 96)]
+    boxes = [ops.BoxList(synthetic.coco_like_boxes(gen, 12, 64, 96, 8.0, 60.0).cuda(), (96, 64))]
+    out = ops.Pooler("ROIAlign", (7, 7), SCALES, 2)(feats, boxes)
+    assert out.dtype == torch.float16 and out.shape == (12, 16, 7, 7)
