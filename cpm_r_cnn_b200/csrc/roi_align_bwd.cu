@@ -210,54 +210,65 @@ __device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const floa
   }
 }
 
-// One CTA per RoI: the RoI's sample taps along both axes (PH*G + PW*G entries) and the pixel box they reach.
-// taps layout: [K][(PH + PW) * G]  (y taps first); box: [K] int4 {ylo, yhi, xlo, xhi}, ylo > yhi when nothing is reached.
+// 64 threads per RoI: warp 0 builds the y sample taps, warp 1 the x sample taps (P * G <= 32 per axis on this path), plus
+// what the tile kernels need to start from a list instead of a scan:
+//   taps    [K][(PH + PW) * G]  (y taps first)
+//   box     [K] int4 {ylo, yhi, xlo, xhi}: the pixels the taps reach, ylo > yhi when nothing is reached
+//   segid   [K] level * B + image, -1 for an RoI outside the pyramid / batch
+//   rowclip [K][NBy], colclip [K][NBx]: per band of 8 pixel rows (columns) first | last << 8 bin row (column) with a
+//           sample tap inside the band, 1 (first 1 > last 0) when there is none
 __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const float* __restrict__ rois, int PH, int PW, int G,
                                                int aligned, const MapperView& mp, const int* __restrict__ roi_levels,
                                                TapS* __restrict__ taps, int4* __restrict__ box, const int r, const int tid,
-                                               const int nthr, int* __restrict__ rowclip, const int NB) {
+                                               int* __restrict__ segid, int* __restrict__ rowclip, const int NBy,
+                                               int* __restrict__ colclip, const int NBx) {
   const float* roi = rois + 5 * (long)r;
   const int l = roi_level_b(roi, pv, mp, roi_levels, r);
   const int nt = (PH + PW) * G;
   TapS* out = taps + (long)r * nt;
   const bool ok = l >= 0 && l < pv.num_levels && (int)roi[0] >= 0 && (int)roi[0] < pv.batch;
+  const int isx = tid >> 5, ln = tid & 31;             // warp 0: y axis, warp 1: x axis
+  int* clip = isx ? colclip : rowclip;
+  const int NB = isx ? NBx : NBy;
+  if (clip != nullptr)
+    for (int b = ln; b < NB; b += 32) clip[(long)r * NB + b] = 1;
   if (!ok) {
-    if (tid == 0) box[r] = make_int4(1, 0, 1, 0);
+    if (tid == 0) {
+      box[r] = make_int4(1, 0, 1, 0);
+      if (segid) segid[r] = -1;
+    }
     return;
   }
   const int H = pv.H[l], W = pv.W[l];
   const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
+  const int P = isx ? PW : PH;
   TapS mine;
   mine.lo = mine.hi = -1;
   mine.wlo = mine.whi = 0.f;
-  for (int e = tid; e < nt; e += nthr) {
-    const bool isy = e < PH * G;
-    const int k = isy ? e : e - PH * G;
+  for (int k = ln; k < P * G; k += 32) {               // one iteration on the staged path (P * G <= 32)
     const int p = k / G, i = k - p * G;
-    const float start = isy ? g.start_h : g.start_w, bin = isy ? g.bin_h : g.bin_w;
+    const float start = isx ? g.start_w : g.start_h, bin = isx ? g.bin_w : g.bin_h;
     const float v = start + p * bin + static_cast<float>(i + .5f) * bin / static_cast<float>(G);
-    const AxisTap t = axis_tap(v, isy ? H : W);
+    const AxisTap t = axis_tap(v, isx ? W : H);
     TapS o;
     o.lo = t.valid ? t.lo : -1;
     o.hi = t.valid ? t.hi : -1;
     o.wlo = t.wlo;
     o.whi = t.whi;
-    out[e] = o;
-    if (e == tid) mine = o;
+    out[(isx ? PH * G : 0) + k] = o;
+    if (k == ln) mine = o;
   }
-  if (rowclip != nullptr && tid < 32) {
-    // (TMA tile kernel) per band of 8 pixel rows: first | last << 8 bin row with a sample tap inside the band.  The y taps
-    // of the RoI sit on lanes [0, PH * G) of the group's first warp (PH * G <= 32 on this path); they are monotone.
-    const bool v = tid < PH * G && mine.lo >= 0;
-    const unsigned valid = __ballot_sync(0xffffffffu, v);
-    for (int b = tid; b < NB; b += 32) rowclip[(long)r * NB + b] = 1;      // first 1 > last 0: no bin row in the band
+  if (clip != nullptr && P * G <= 32) {
+    // the taps of the axis sit on lanes [0, P * G) and are monotone: per band, the first / last bin with a tap inside
     __syncwarp();
+    const bool v = ln < P * G && mine.lo >= 0;
+    const unsigned valid = __ballot_sync(0xffffffffu, v);
     if (valid) {
-      const int ylo = __shfl_sync(0xffffffffu, mine.lo, __ffs(valid) - 1);
-      const int yhi = __shfl_sync(0xffffffffu, mine.hi, 31 - __clz(valid));
-      for (int b = ylo >> 3; b <= (yhi >> 3) && b < NB; b++) {
+      const int lo0 = __shfl_sync(0xffffffffu, mine.lo, __ffs(valid) - 1);
+      const int hi1 = __shfl_sync(0xffffffffu, mine.hi, 31 - __clz(valid));
+      for (int b = lo0 >> 3; b <= (hi1 >> 3) && b < NB; b++) {
         const unsigned m = __ballot_sync(0xffffffffu, v && mine.hi >= 8 * b && mine.lo < 8 * b + 8);
-        if (tid == 0 && m) rowclip[(long)r * NB + b] = ((__ffs(m) - 1) / G) | (((31 - __clz(m)) / G) << 8);
+        if (ln == 0 && m) clip[(long)r * NB + b] = ((__ffs(m) - 1) / G) | (((31 - __clz(m)) / G) << 8);
       }
     }
   }
@@ -271,6 +282,7 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
     const int ylo = yf <= 0.f ? 0 : min((int)yf, H - 1), yhi = yl >= (float)(H - 1) ? H - 1 : (int)fmaxf(yl, 0.f) + 1;
     const int xlo = xf <= 0.f ? 0 : min((int)xf, W - 1), xhi = xl >= (float)(W - 1) ? W - 1 : (int)fmaxf(xl, 0.f) + 1;
     box[r] = none ? make_int4(1, 0, 1, 0) : make_int4(ylo, yhi, xlo, xhi);
+    if (segid) segid[r] = l * pv.batch + (int)roi[0];
   }
 }
 
@@ -279,15 +291,66 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
 __global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* __restrict__ rois, int K, int PH, int PW, int G,
                                                     int aligned, MapperView mp, const int* __restrict__ roi_levels,
                                                     int* __restrict__ seg_count, int* __restrict__ perm,
-                                                    TapS* __restrict__ taps, int4* __restrict__ box, int* __restrict__ rowclip,
-                                                    int NB) {
+                                                    TapS* __restrict__ taps, int4* __restrict__ box, int* __restrict__ segid,
+                                                    int* __restrict__ rowclip, int NBy, int* __restrict__ colclip, int NBx) {
   const int nseg = pv.num_levels * pv.batch;
   if ((int)blockIdx.x < nseg) {
     bin_rois_block(pv, rois, K, mp, roi_levels, seg_count, perm, blockIdx.x);
   } else {
     const int r = 4 * ((int)blockIdx.x - nseg) + (threadIdx.x >> 6);
-    if (r < K) roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, 64, rowclip, NB);
+    if (r < K)
+      roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, segid, rowclip, NBy, colclip,
+                     NBx);
   }
+}
+
+// Per 8x8-pixel tile (one warp each, launch order of the tile kernel): the RoIs that reach the tile, in RoI order, with
+// the bin rows / columns that have a sample tap inside it -- what a tile CTA would otherwise find by scanning its
+// (level, image) list and reading every candidate's taps.  At most kCandCap entries are stored; a busier tile (count >
+// kCandCap) is scanned by its CTAs as before.
+constexpr int kCandCap = 64;
+
+__global__ void __launch_bounds__(256) bwd_tile_cands(PyramidView pv, TileGrid tg, int K, const int4* __restrict__ box,
+                                                       const int* __restrict__ segid, const int* __restrict__ rowclip, int NBy,
+                                                       const int* __restrict__ colclip, int NBx, int* __restrict__ tile_count,
+                                                       int2* __restrict__ cands, int ntiles) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= ntiles) return;
+  const TileId id = decode_tile(tg, pv.num_levels, t, 8, 8);
+  const int seg = id.l * pv.batch + id.b;
+  const int by = id.y0 >> 3, bx = id.x0 >> 3;
+  int2* out = cands + (long)t * kCandCap;
+  int cnt = 0;
+  for (int base = 0; base < K; base += 128) {
+    int sg[4];
+    int4 bxv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = base + 32 * u + lane;
+      sg[u] = r < K ? __ldg(segid + r) : -1;
+      bxv[u] = r < K ? __ldg(box + r) : make_int4(1, 0, 1, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (base + 32 * u >= K) break;
+      const int r = base + 32 * u + lane;
+      const int4 b4 = bxv[u];
+      bool hit = sg[u] == seg && b4.x <= b4.y && b4.x < id.y0 + 8 && b4.y >= id.y0 && b4.z < id.x0 + 8 && b4.w >= id.x0;
+      int cr = 0;
+      if (hit) {
+        const int rc = by < NBy ? __ldg(rowclip + (long)r * NBy + by) : 1;
+        const int cc = bx < NBx ? __ldg(colclip + (long)r * NBx + bx) : 1;
+        hit = (rc & 255) <= (rc >> 8) && (cc & 255) <= (cc >> 8);
+        cr = (rc & 255) | ((rc >> 8) << 8) | ((cc & 255) << 16) | ((cc >> 8) << 24);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1));
+      if (hit && pos < kCandCap) out[pos] = make_int2(r, cr);
+      cnt += __popc(bal);
+    }
+  }
+  if (lane == 0) tile_count[t] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -369,13 +432,15 @@ template <bool GO_CL, int PC, int GC>
 __global__ void __launch_bounds__(kTileThreads, 3)
 bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, const TapS* __restrict__ taps,
                  const int4* __restrict__ box, int K, int PH_, int PW_, int G_, const int* __restrict__ seg_count,
-                 const int* __restrict__ perm, int chunks) {
+                 const int* __restrict__ perm, int chunks, const int* __restrict__ tile_count,
+                 const int2* __restrict__ cands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int PH = PC ? PC : PH_, PW = PC ? PC : PW_, G = GC ? GC : G_;
   const int C = pv.channels;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int t = blockIdx.x / chunks;
+  const int tile_id = t;
   const int c0 = (blockIdx.x % chunks) * kChunk;
   int oi = 0;
   while (oi + 1 < pv.num_levels && t >= tg.first[oi + 1]) oi++;
@@ -397,8 +462,12 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
 #pragma unroll
   for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
 
+  // the tile's candidates: prepared by bwd_tile_cands (RoI + clipped bin ranges; one load), or -- a tile busier than the
+  // prepared list holds, or a call without the lists -- found by scanning the (level, image) RoI list
+  const int pc = tile_count ? tile_count[tile_id] : -1;
+  const bool prepared = pc >= 0 && pc <= kCandCap;
   const int seg = l * pv.batch + b;
-  const int nseg = seg_count[seg];
+  const int nseg = prepared ? pc : seg_count[seg];
   const int* plist = perm + (long)seg * K;
 
   // staging constants of this thread
@@ -410,6 +479,16 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
   constexpr uint32_t kBufBytes = NBUF * SROW * 4;
 
   for (int base = 0; base < nseg; base += kRound) {
+    int ncand = 0;
+    if (prepared) {
+      if ((int)threadIdx.x < pc) {
+        const int2 e = __ldg(cands + (long)tile_id * kCandCap + threadIdx.x);
+        sm.cand[threadIdx.x] = e.x;
+        sm.crange[threadIdx.x] = e.y;
+      }
+      ncand = pc;
+      __syncthreads();
+    } else {
     // ---- RoIs of this (level, image) whose reach intersects the tile, in RoI order (two list entries per thread) ----
     bool hit[2] = {false, false};
     int me[2] = {-1, -1};
@@ -426,7 +505,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
     if (lane == 0) sm.wsum[warp] = __popc(bal0) + __popc(bal1);
     __syncthreads();
     const unsigned below = (1u << lane) - 1;
-    int pos = __popc(bal0 & below) + __popc(bal1 & below), ncand = 0;
+    int pos = __popc(bal0 & below) + __popc(bal1 & below);
     for (int w = 0; w < 8; w++) {
       if (w < warp) pos += sm.wsum[w];
       ncand += sm.wsum[w];
@@ -459,6 +538,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
       }
     }
     __syncthreads();
+    }
 
     // ---- the sub-blocks ("items") of the round: thread 0 walks the candidates and publishes descriptors two items
     //      ahead in a 4-slot ring; everybody else only reads them ----
@@ -656,7 +736,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
 }
 
 typedef void (*StagedFn)(PyramidView, TileGrid, const float*, const TapS*, const int4*, int, int, int, int, const int*,
-                         const int*, int);
+                         const int*, int, const int*, const int2*);
 
 template <bool GO_CL>
 static StagedFn pick_staged(int PH, int PW, int G) {
@@ -674,16 +754,17 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 using namespace cpm;
 
 struct BwdWs {
-  size_t seg_count, perm, taps, box, rowclip, tile_count, tile_off, lists, total;
+  size_t seg_count, perm, taps, box, segid, rowclip, colclip, tile_count, cands, tile_off, lists, total;
+  int NBy, NBx;          // bands of 8 pixel rows / columns of the largest level (clip table widths); 0: no clip tables
+  long tiles8;           // 8x8 tiles of the pyramid
 };
 
 // the single-pass staged kernel takes every fixed-grid pooler whose samples per axis fit one ballot
 static bool bwd_staged_ok(int PH, int PW, int G) { return G >= 1 && PH * G <= 32 && PW * G <= 32; }
 
 // Which deterministic tile kernel takes a call (measured on the benchmark workload): the staged
-// 8x8-tile kernel -- NHWC pyramid 7x7 0.135 ms / 14x14 0.231 ms, NCHW pyramid 0.152 / 0.252 ms; the TMA tile kernel
-// measures 0.139 / 0.362 ms (NHWC) and 0.152 / 0.385 ms (NCHW).  CPM_BWD_IMPL=tma selects the latter for the two CPM
-// poolers (A/B measurements); read once per process.
+// 8x8-tile kernel; CPM_BWD_IMPL=tma selects the TMA tile kernel for the two CPM poolers (measured slower; kept for A/B
+// measurements).  Read once per process.
 static int bwd_impl_env() {
   static const int v = [] {
     const char* e = getenv("CPM_BWD_IMPL");
@@ -694,43 +775,56 @@ static int bwd_impl_env() {
   return v;
 }
 
-// tiles > 0: with the per-tile candidate lists of the TMA kernel
-static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, long tiles, size_t list_entries, int bands = 0) {
-  BwdWs w;
-  const size_t segs = (size_t)(L > 0 ? L : 1) * (size_t)(B > 0 ? B : 1);
-  const size_t k = (size_t)(K > 0 ? K : 1);
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-  w.seg_count = take(segs * sizeof(int));
-  w.perm = take(segs * k * sizeof(int));
-  w.taps = take(k * (size_t)(PH + PW) * (size_t)(G > 0 ? G : 1) * sizeof(TapS));
-  w.box = take(k * sizeof(int4));
-  w.rowclip = take(tiles > 0 ? k * (size_t)bands * sizeof(int) : 0);
-  w.tile_count = take((size_t)tiles * sizeof(int));
-  w.tile_off = take((size_t)tiles * sizeof(int));
-  w.lists = take(list_entries * sizeof(int2));
-  w.total = off;
-  return w;
-}
-
 static bool tma_shape_ok(const cpm_pyramid_t* p, int PH, int PW, int G) {
   if (!(btma::shape_ok(PH, PW, G) && p->dtype == CPM_F32 && p->channels % btma::CH == 0)) return false;
   return bwd_impl_env() == 1;
 }
 
+// p == nullptr: the plain layout (no clip tables, no per-tile lists: tile CTAs scan); else with the prepared per-tile
+// candidate lists of the staged kernel and, when `tma`, the stage lists of the TMA kernel
+static BwdWs bwd_layout(int64_t K, int L, int B, int PH, int PW, int G, const cpm_pyramid_t* p, bool tma) {
+  BwdWs w;
+  const size_t segs = (size_t)(L > 0 ? L : 1) * (size_t)(B > 0 ? B : 1);
+  const size_t k = (size_t)(K > 0 ? K : 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  w.NBy = w.NBx = 0;
+  w.tiles8 = 0;
+  if (p != nullptr && bwd_staged_ok(PH, PW, G)) {
+    for (int l = 0; l < p->num_levels; l++) {
+      const int by = (p->height[l] + 7) / 8, bx = (p->width[l] + 7) / 8;
+      w.NBy = by > w.NBy ? by : w.NBy;
+      w.NBx = bx > w.NBx ? bx : w.NBx;
+      w.tiles8 += (long)p->batch * by * bx;
+    }
+  }
+  const long tma_tiles = (p != nullptr && tma) ? btma::num_tiles(p) : 0;
+  w.seg_count = take(segs * sizeof(int));
+  w.perm = take(segs * k * sizeof(int));
+  w.taps = take(k * (size_t)(PH + PW) * (size_t)(G > 0 ? G : 1) * sizeof(TapS));
+  w.box = take(k * sizeof(int4));
+  w.segid = take(w.NBy ? k * sizeof(int) : 0);
+  w.rowclip = take(k * (size_t)w.NBy * sizeof(int));
+  w.colclip = take(k * (size_t)w.NBx * sizeof(int));
+  w.tile_count = take((size_t)(w.tiles8 > tma_tiles ? w.tiles8 : tma_tiles) * sizeof(int));
+  w.cands = take((size_t)w.tiles8 * kCandCap * sizeof(int2));
+  w.tile_off = take((size_t)tma_tiles * sizeof(int));
+  w.lists = take(tma_tiles > 0 ? btma::list_entries(p, K, PH) * sizeof(int2) : 0);
+  w.total = off;
+  return w;
+}
+
 extern "C" size_t cpm_roi_align_backward_workspace_bytes(int64_t K, int num_levels, int batch, int channels, int pooled_h,
                                                          int pooled_w, int sampling_ratio) {
   (void)channels;
-  return bwd_layout(K, num_levels, batch, pooled_h, pooled_w, sampling_ratio, 0, 0).total;
+  return bwd_layout(K, num_levels, batch, pooled_h, pooled_w, sampling_ratio, nullptr, false).total;
 }
 
 extern "C" size_t cpm_roi_align_backward_workspace_bytes_pyr(const cpm_pyramid_t* grad_feat, int64_t K, int pooled_h,
                                                              int pooled_w, int sampling_ratio) {
   if (grad_feat == nullptr || grad_feat->num_levels < 1 || grad_feat->num_levels > CPM_MAX_LEVELS) return 0;
-  if (tma_shape_ok(grad_feat, pooled_h, pooled_w, sampling_ratio))
-    return bwd_layout(K, grad_feat->num_levels, grad_feat->batch, pooled_h, pooled_w, sampling_ratio,
-                      btma::num_tiles(grad_feat), btma::list_entries(grad_feat, K, pooled_h), btma::num_bands(grad_feat)).total;
-  return bwd_layout(K, grad_feat->num_levels, grad_feat->batch, pooled_h, pooled_w, sampling_ratio, 0, 0).total;
+  return bwd_layout(K, grad_feat->num_levels, grad_feat->batch, pooled_h, pooled_w, sampling_ratio, grad_feat,
+                    tma_shape_ok(grad_feat, pooled_h, pooled_w, sampling_ratio)).total;
 }
 
 extern "C" int cpm_roi_align_backward(const cpm_pyramid_t* grad_feat, const void* d_grad_out, const void* d_rois, int64_t K,
@@ -789,13 +883,12 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     bool tma = pooled_layout == CPM_POOLED_KCHW && interpolation == CPM_INTERP_BILINEAR &&
                tma_shape_ok(grad_feat, pooled_h, pooled_w, sampling_ratio) && ((uintptr_t)d_grad_out & 15) == 0;
     for (int l = 0; tma && l < L; l++) tma = ((uintptr_t)grad_feat->d_level[l] & 15) == 0;
-    BwdWs w = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, 0, 0);
-    if (tma) {
-      const size_t entries = btma::list_entries(grad_feat, K, pooled_h);
-      const BwdWs wt = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, btma::num_tiles(grad_feat), entries,
-                                  btma::num_bands(grad_feat));
-      if (entries < (1ull << 31) && d_workspace != nullptr && workspace_bytes >= wt.total) w = wt;
-      else tma = false;      // sized with the plain query: the generic staged kernel takes the call
+    // a workspace sized with the plain query (no pyramid shapes) has no room for the per-tile lists: tile CTAs then scan
+    BwdWs w = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, grad_feat, tma);
+    if (tma && btma::list_entries(grad_feat, K, pooled_h) >= (1ull << 31)) tma = false;
+    if (d_workspace == nullptr || workspace_bytes < w.total || (long)w.tiles8 * kCandCap >= (1L << 31)) {
+      tma = false;
+      w = bwd_layout(K, L, B, pooled_h, pooled_w, sampling_ratio, nullptr, false);
     }
     if (!tma && !(fast_f32 && bwd_staged_ok(pooled_h, pooled_w, sampling_ratio))) {
       set_error("deterministic backward needs an fp32 gradient pyramid (NHWC or NCHW, 16-byte aligned levels), bilinear "
@@ -815,17 +908,17 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     int4* box = (int4*)(wsb + w.box);
     const int Kp = K > 0 ? (int)K : 1;
     if (K > 0) {
-      bwd_prepare<<<(unsigned)(L * B + (K + 3) / 4), 256, 0, st>>>(pv, (const float*)d_rois, (int)K, pooled_h, pooled_w,
-                                                                    sampling_ratio, aligned, mp, d_roi_levels, seg_count,
-                                                                    perm, taps, box, tma ? (int*)(wsb + w.rowclip) : nullptr,
-                                                                    tma ? btma::num_bands(grad_feat) : 0);
+      bwd_prepare<<<(unsigned)(L * B + (K + 3) / 4), 256, 0, st>>>(
+          pv, (const float*)d_rois, (int)K, pooled_h, pooled_w, sampling_ratio, aligned, mp, d_roi_levels, seg_count, perm, taps,
+          box, w.NBy ? (int*)(wsb + w.segid) : nullptr, w.NBy ? (int*)(wsb + w.rowclip) : nullptr, w.NBy,
+          w.NBx ? (int*)(wsb + w.colclip) : nullptr, w.NBx);
       CPM_CHECK_LAUNCH();
     } else {
       CPM_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, (size_t)L * B * sizeof(int), st));
     }
     if (tma) {
       rc = btma::launch(grad_feat, pv, (const float*)d_grad_out, (int)K, pooled_h, taps, box, (const int*)(wsb + w.rowclip),
-                        seg_count, perm, (int*)(wsb + w.tile_count), (int*)(wsb + w.tile_off), (int2*)(wsb + w.lists), st);
+                        w.NBy, seg_count, perm, (int*)(wsb + w.tile_count), (int*)(wsb + w.tile_off), (int2*)(wsb + w.lists), st);
       if (rc != CPM_ERR_UNSUPPORTED) return rc;
       // no tensor-map encoder in this driver: the generic staged kernel below
     }
@@ -849,8 +942,17 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
         }
       }
     }
+    const bool lists = w.NBy > 0 && K > 0;
+    if (lists) {
+      bwd_tile_cands<<<(unsigned)((tiles + 7) / 8), 256, 0, st>>>(pv, tg, (int)K, box, (const int*)(wsb + w.segid),
+                                                                 (const int*)(wsb + w.rowclip), w.NBy,
+                                                                 (const int*)(wsb + w.colclip), w.NBx,
+                                                                 (int*)(wsb + w.tile_count), (int2*)(wsb + w.cands), (int)tiles);
+      CPM_CHECK_LAUNCH();
+    }
     fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
-        pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks);
+        pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks,
+        lists ? (const int*)(wsb + w.tile_count) : nullptr, lists ? (const int2*)(wsb + w.cands) : nullptr);
     CPM_CHECK_LAUNCH();
     return CPM_OK;
   }

@@ -99,12 +99,11 @@ inline bool shape_ok(int PH, int PW, int G) { return G == 2 && PH == PW && (PH =
 // <= max tiles of a level * K * ceil(P / rows per stage)
 size_t list_entries(const cpm_pyramid_t* p, int64_t K, int P);
 long num_tiles(const cpm_pyramid_t* p);
-int num_bands(const cpm_pyramid_t* p);     // bands of TH pixel rows of the tallest level (row-clip table width)
 // builds the per-tile stage lists (after bwd_prepare) and runs the tile kernel; returns CPM_ERR_UNSUPPORTED when the
 // driver cannot encode the tensor maps (the caller then takes the generic staged kernel)
 int launch(const cpm_pyramid_t* grad_feat, const PyramidView& pv, const float* go, int K, int P, const TapS* taps,
-           const int4* box, const int* rowclip, const int* seg_count, const int* perm, int* tile_count, int* tile_off,
-           int2* lists, cudaStream_t st);
+           const int4* box, const int* rowclip, int NB, const int* seg_count, const int* perm, int* tile_count,
+           int* tile_off, int2* lists, cudaStream_t st);
 }  // namespace btma
 
 }  // namespace cpm

@@ -454,12 +454,6 @@ long num_tiles(const cpm_pyramid_t* p) {
   return make_tile_grid(tg, p, TH, TW);
 }
 
-int num_bands(const cpm_pyramid_t* p) {
-  int mx = 1;
-  for (int l = 0; l < p->num_levels; l++) mx = max(mx, (p->height[l] + TH - 1) / TH);
-  return mx;
-}
-
 size_t list_entries(const cpm_pyramid_t* p, int64_t K, int P) {
   long mx = 1;
   for (int l = 0; l < p->num_levels; l++) {
@@ -489,8 +483,8 @@ static int launch_tiles(const CUtensorMap* tm, const PyramidView& pv, const Tile
 }
 
 int launch(const cpm_pyramid_t* grad_feat, const PyramidView& pv, const float* go, int K, int P, const TapS* taps,
-           const int4* box, const int* rowclip, const int* seg_count, const int* perm, int* tile_count, int* tile_off,
-           int2* lists, cudaStream_t st) {
+           const int4* box, const int* rowclip, int NB, const int* seg_count, const int* perm, int* tile_count,
+           int* tile_off, int2* lists, cudaStream_t st) {
   const int C = grad_feat->channels;
   TileGrid tg;
   const long tiles = make_tile_grid(tg, grad_feat, TH, TW);
@@ -519,7 +513,6 @@ int launch(const cpm_pyramid_t* grad_feat, const PyramidView& pv, const float* g
       }
     }
   }
-  const int NB = num_bands(grad_feat);
   if (P == 14)
     bwd_tile_lists<14><<<(unsigned)((tiles + 7) / 8), 256, 0, st>>>(pv, tg, K > 0 ? K : 1, box, rowclip, NB, seg_count, perm,
                                                                    tile_count, tile_off, lists, (int)tiles);
