@@ -484,7 +484,7 @@ def run_ours(args):
     # ---- pieces of the NCHW step, one graph each: the staging alone, the backward writing NCHW ----
     nchw_ms = {}
     try:
-        st_fn = lambda: [ra.stage_nhwc(f, cache=False) for f in feats_nchw]
+        st_fn = lambda: ra.stage_pyramid_nhwc(feats_nchw, cache=False)
         b_fns = [op_bwd(p, go, nchw_grad=True) for p, go in zip(POOLERS, gouts)]
         warm([st_fn] + b_fns, 2)
         caps = [capture(fn) for fn in [st_fn] + b_fns]

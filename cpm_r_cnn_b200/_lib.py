@@ -61,6 +61,7 @@ _SIGNATURES = {
                                      ctypes.c_void_p]),
     "cpm_layout_convert": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "cpm_layout_convert_pyramid": (ctypes.c_int, [ctypes.POINTER(Pyramid), ctypes.POINTER(Pyramid), ctypes.c_void_p]),
     "cpm_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64]),
     "cpm_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float,
                                ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

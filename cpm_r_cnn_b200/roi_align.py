@@ -40,8 +40,8 @@ class _StagingCache(object):
         self.entries = []                # (weakref to source, version, staged), most recent last
         self.hits = self.misses = 0
 
-    def get(self, x):
-        import weakref
+    def lookup(self, x):
+        """The cached NHWC copy of tensor object `x` at its current version, or None (dead / stale entries are dropped)."""
         alive = []
         found = None
         for ref, ver, staged in self.entries:
@@ -56,12 +56,20 @@ class _StagingCache(object):
         self.entries = alive
         if found is not None:
             self.hits += 1
-            return found
+        return found
+
+    def put(self, x, staged):
+        import weakref
         self.misses += 1
-        staged = _stage_uncached(x)
         self.entries.append((weakref.ref(x), x._version, staged))
         if len(self.entries) > self.capacity:
             self.entries = self.entries[-self.capacity:]
+
+    def get(self, x):
+        staged = self.lookup(x)
+        if staged is None:
+            staged = _stage_uncached(x)
+            self.put(x, staged)
         return staged
 
     def clear(self):
@@ -107,13 +115,46 @@ def make_pyramid(levels, scales, layout):
     return p
 
 
+def stage_pyramid_nhwc(levels, cache=True):
+    """NHWC copies of all levels: cached copies are reused, the missing fp32 levels are staged in ONE launch
+    (cpm_layout_convert_pyramid)."""
+    out = [None] * len(levels)
+    todo = []
+    for i, t in enumerate(levels):
+        _lib.require_cuda(t, "input")
+        if _is_nhwc(t):
+            out[i] = t
+        else:
+            hit = STAGING_CACHE.lookup(t) if cache else None
+            if hit is not None:
+                out[i] = hit
+            else:
+                todo.append(i)
+    fused = [i for i in todo if levels[i].dtype == torch.float32 and levels[i].is_contiguous()
+             and levels[i].shape[:2] == levels[todo[0]].shape[:2]]
+    if len(fused) > 1:
+        srcs = [levels[i] for i in fused]
+        dsts = [torch.empty(t.shape, dtype=t.dtype, device=t.device, memory_format=torch.channels_last) for t in srcs]
+        ones = [1.0] * len(srcs)
+        ps, pd = make_pyramid(srcs, ones, _lib.NCHW), make_pyramid(dsts, ones, _lib.NHWC)
+        with _lib.device_of(srcs[0]):
+            _lib.check(_lib.lib().cpm_layout_convert_pyramid(ctypes.byref(ps), ctypes.byref(pd),
+                                                             _lib.stream_ptr(srcs[0].device)))
+        for i, d in zip(fused, dsts):
+            out[i] = d
+            if cache:
+                STAGING_CACHE.put(levels[i], d)
+    for i in todo:
+        if out[i] is None:
+            out[i] = stage_nhwc(levels[i], cache)
+    return out
+
+
 def _prepare_levels(levels, interpolation):
     """-> (tensors kept alive, layout).  fp32 bilinear goes to NHWC (staging NCHW inputs); the rest stays NCHW."""
     dt = levels[0].dtype
-    if dt == torch.float32 and interpolation == 0 and levels[0].shape[1] % 4 == 0:
-        return [stage_nhwc(t) for t in levels], _lib.NHWC
-    if dt == torch.bfloat16:
-        return [stage_nhwc(t) for t in levels], _lib.NHWC
+    if (dt == torch.float32 and interpolation == 0 and levels[0].shape[1] % 4 == 0) or dt == torch.bfloat16:
+        return stage_pyramid_nhwc(levels), _lib.NHWC
     return [t.contiguous() for t in levels], _lib.NCHW
 
 

@@ -163,6 +163,10 @@ CPM_API int cpm_level_map(const float* d_rois, int64_t K, const cpm_level_mapper
  * The fast RoIAlign kernels read/write NHWC; torch.channels_last tensors need no staging at all. */
 CPM_API int cpm_layout_convert(const void* d_src, void* d_dst, int batch, int channels, int height, int width, int dtype,
                        int to_layout, void* stream);
+/* A whole pyramid in ONE launch (what Pooler.forward does for the NCHW maps the reference's FPN emits, FPN.py:96-121): `src`
+ * and `dst` describe the same levels in the two layouts.  fp32 with 16-byte aligned levels takes a 16-byte-vectorised tile
+ * transpose; anything else falls back to one cpm_layout_convert per level. */
+CPM_API int cpm_layout_convert_pyramid(const cpm_pyramid_t* src, const cpm_pyramid_t* dst, void* stream);
 
 /* ---- NMS ------------------------------------------------------------------------------------------
  * Hard NMS over N boxes (x1,y1,x2,y2), fp32.  Replaces

@@ -295,6 +295,19 @@ def test_layout_staging_roundtrip():
     assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(x, y)
 
 
+@pytest.mark.parametrize("C", [256, 72, 37])
+def test_fused_pyramid_staging(C):
+    """cpm_layout_convert_pyramid: all NCHW levels of a pyramid to NHWC in one launch (16-byte accesses; ragged tiles,
+    channel counts and map sizes that are not multiples of 4 take the scalar tails)."""
+    import importlib
+    ra = importlib.import_module("cpm_r_cnn_b200.roi_align")
+    gen = torch.Generator().manual_seed(4)
+    levels = [torch.randn(2, C, h, w, generator=gen).cuda() for h, w in ((50, 84), (25, 42), (13, 21), (7, 11))]
+    staged = ra.stage_pyramid_nhwc(levels, cache=False)
+    for x, y in zip(levels, staged):
+        assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(x, y)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # NMS
 # ----------------------------------------------------------------------------------------------------------------
