@@ -37,7 +37,6 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
   const float inter = __fmul_rn(w, h);
-  if (inter == 0.f && thr >= 0.f) return false;   // 0/u and 0/0 (NaN) both compare false
   const float aw = __fsub_rn(a.z, a.x), ah = __fsub_rn(a.w, a.y);
   const float bw = __fsub_rn(b.z, b.x), bh = __fsub_rn(b.w, b.y);
   float uni;
@@ -48,6 +47,17 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
   } else {
     uni = __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter);
   }
+  // The reference's decision is  fl(inter / uni) > thr.  Away from the threshold it follows from one multiplication: with
+  // t = fl(thr * uni) (relative error 2^-24) and a guard band of 2^-20, inter outside [t (1 - 2^-20), t (1 + 2^-20)] decides
+  // the rounded quotient's comparison as well -- branch-free for all but the pairs inside the band (and degenerate unions),
+  // which take the exact IEEE division.  (A warp tests 32 rows against one column: with the division on the common path,
+  // one overlapping lane made all 32 pay for it.)
+  const float t = __fmul_rn(thr, uni);
+  const float t1 = __fmul_rn(t, 1.00000095367431640625f), t0 = __fmul_rn(t, 0.99999904632568359375f);
+  const bool pos = uni > 0.f && thr >= 0.f;
+  if (pos && inter > t1) return true;
+  if (pos && inter < t0) return false;
+  if (inter == 0.f && thr >= 0.f) return false;   // 0/u and 0/0 (NaN) both compare false
   return __fdiv_rn(inter, uni) > thr;
 }
 
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
                                                             long long topk, int flavor, unsigned char* __restrict__ flags,
                                                             long long* __restrict__ seg_counts,
                                                             unsigned long long* __restrict__ total_kept,
-                                                            unsigned* __restrict__ rem_g, long long trash) {
+                                                            unsigned* __restrict__ rem_g, long long trash, int skip_upto) {
   __shared__ float4 sb[kSweepCap];
   __shared__ unsigned rem_s[kSweepMaxSeg / 32];
   __shared__ unsigned long long diag[64];
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
     const int beg = starts[s];
     const int end = s + 1 < nseg ? starts[s + 1] : N;
     const int n = end - beg;
+    if (n <= skip_upto) continue;         // taken by the bitmask path (nms_mask + nms_sweep_mask)
     if (trash >= 0 && (long long)(keys[beg] >> 32) >= trash) {      // boxes with an out-of-range segment id: all dropped
       for (int j = tid; j < n; j += kSweepThreads) flags[beg + j] = 0;
       continue;
@@ -229,6 +240,145 @@ __global__ void __launch_bounds__(WIDE ? 1024 : 256, 1) nms_sweep(const float4* 
   }
 }
 
+// ---- bitmask path: few large segments (RPN: image x level, ~1000 boxes each) ---------------------------------------
+// The phased sweep above keeps one segment on one SM; with 80 segments more than a third of the machine idles.  Here the
+// IoU tests of a segment are spread over the grid: nms_mask writes, per sorted box, one 64-bit word per 64-box column
+// tile to its right (shared-memory box tiles; the reference's mask kernel, ml_nms.cu:29-78, without the D2H copy), and
+// nms_sweep_mask resolves a segment with ONE warp (ml_nms.cu:127-140 on the device).
+constexpr int kMaskWords = 32;                     // row stride: segments up to 2048 boxes
+constexpr int kMaskMaxSeg = 64 * kMaskWords;
+constexpr long long kMaskMaxN = 131072;            // 256 bytes of mask per box: 32 MB of workspace at most
+
+__global__ void __launch_bounds__(256) nms_mask(const float4* __restrict__ sboxes, const int* __restrict__ starts,
+                                                 const int* __restrict__ d_nseg, int N,
+                                                 const unsigned long long* __restrict__ keys, float thr, int flavor,
+                                                 long long trash, unsigned long long* __restrict__ mask) {
+  __shared__ float4 cb[4][64];
+  const int s = blockIdx.x;
+  const int nseg = *d_nseg;
+  if (s >= nseg) return;
+  const int beg = starts[s];
+  const int n = (s + 1 < nseg ? starts[s + 1] : N) - beg;
+  const int rt = blockIdx.y;
+  if (n > kMaskMaxSeg || rt * 64 >= n) return;
+  if (trash >= 0 && (long long)(keys[beg] >> 32) >= trash) return;
+  const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int row = rt * 64 + r;
+  const float4 a = row < n ? sboxes[beg + row] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nt = (n + 63) >> 6;
+  for (int jt = rt + g; jt < nt; jt += 4) {
+    const int col = jt * 64 + r;
+    cb[g][r] = col < n ? sboxes[beg + col] : make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
+    unsigned long long bits = 0ull;
+    const int j0 = jt == rt ? r + 1 : 0, j1 = min(64, n - jt * 64);
+    if (row < n)
+      for (int j = j0; j < j1; j++)
+        if (iou_gt(a, cb[g][j], thr, flavor)) bits |= 1ull << j;
+    if (row < n) mask[(size_t)(beg + row) * kMaskWords + jt] = bits;
+    asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
+  }
+}
+
+// One warp (one CTA) per segment.  The mask rows of a 64-box phase -- the words from the phase's own column tile to the
+// right end -- are staged in shared memory with cp.async one phase ahead; the phase is resolved on registers (every lane
+// holds the 64 diagonal words; `alive` and `kept` are warp-uniform, no shuffles in the chain), then lane w ORs the rows of
+// the kept boxes into word w of the suppressed bitmap.
+__global__ void __launch_bounds__(32) nms_sweep_mask(const int* __restrict__ starts, const int* __restrict__ d_nseg, int N,
+                                                      const unsigned long long* __restrict__ keys, long long topk,
+                                                      long long trash, const unsigned long long* __restrict__ mask,
+                                                      unsigned char* __restrict__ flags, long long* __restrict__ seg_counts,
+                                                      unsigned long long* __restrict__ total_kept) {
+  __shared__ __align__(16) unsigned long long sm[2][64][kMaskWords];     // 32 KB
+  const int lane = threadIdx.x;
+  const int s = blockIdx.x;
+  const int nseg = *d_nseg;
+  if (s >= nseg) return;
+  const int beg = starts[s];
+  const int n = (s + 1 < nseg ? starts[s + 1] : N) - beg;
+  if (n > kMaskMaxSeg) return;
+  if (trash >= 0 && (long long)(keys[beg] >> 32) >= trash) {
+    for (int j = lane; j < n; j += 32) flags[beg + j] = 0;
+    return;
+  }
+  const int nt = (n + 63) >> 6;
+  const unsigned long long* mrow = mask + (size_t)beg * kMaskWords;
+  auto stage = [&](int ph, int buf) {
+    const int base = ph * 64, m = min(64, n - base);
+    const int c0 = ph >> 1, c1 = (nt + 1) >> 1;            // 16-byte chunks (word pairs) holding words ph .. nt-1
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int r = lane + 32 * h;
+      if (r < m) {
+        const unsigned long long* g = mrow + (size_t)(base + r) * kMaskWords;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sm[buf][r][0]);
+        for (int c = c0; c < c1; c++)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * c), "l"(g + 2 * c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  unsigned long long remv = 0ull;                  // word `lane` of the segment's suppressed bitmap
+  long long kept_total = 0;
+  stage(0, 0);
+  for (int ph = 0; ph < nt; ph++) {
+    const int base = ph * 64, buf = ph & 1;
+    const int m = min(64, n - base);
+    if (ph + 1 < nt) {
+      stage(ph + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned long long row[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) row[i] = sm[buf][i][ph];          // rows >= m are never consulted (alive is masked)
+    unsigned long long alive = ~__shfl_sync(0xffffffffu, remv, ph);
+    if (m < 64) alive &= (1ull << m) - 1;
+    unsigned long long kept = 0ull;
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      if ((alive >> i) & 1ull) {
+        kept |= 1ull << i;
+        alive &= ~row[i];
+      }
+    }
+    bool done = false;
+    if (topk > 0 && kept_total + __popcll(kept) >= topk) {   // ml_nms.cu:134: stop after topk keeps
+      long long room = topk - kept_total;
+      unsigned long long k2 = 0ull, k = kept;
+      while (room > 0 && k) {
+        k2 |= k & (~k + 1);
+        k &= k - 1;
+        room--;
+      }
+      kept = k2;
+      done = true;
+    }
+    if (lane < m) flags[beg + base + lane] = (unsigned char)((kept >> lane) & 1ull);
+    if (lane + 32 < m) flags[beg + base + lane + 32] = (unsigned char)((kept >> (lane + 32)) & 1ull);
+    kept_total += __popcll(kept);
+    if (done) {
+      for (int j = base + 64 + lane; j < n; j += 32) flags[beg + j] = 0;
+      break;
+    }
+    if (lane > ph && lane < nt) {                  // rows of the kept boxes -> word `lane` (kept is warp-uniform)
+      unsigned long long o = 0ull;
+#pragma unroll
+      for (int i = 0; i < 64; i++)
+        if ((kept >> i) & 1ull) o |= sm[buf][i][lane];
+      remv |= o;
+    }
+    __syncwarp();                                  // the buffer is restaged two phases later
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (lane == 0) {
+    if (seg_counts) seg_counts[keys[beg] >> 32] = kept_total;
+    if (total_kept) atomicAdd(total_kept, (unsigned long long)kept_total);
+  }
+}
+
 // ml_nms: kept boxes re-keyed by (descending score, ascending input index); dropped boxes sort to the end
 __global__ void nms_rekey(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
                           const unsigned char* __restrict__ flags, int N, unsigned long long* __restrict__ keys2) {
@@ -252,7 +402,7 @@ struct ToI64 {
 
 // ---- workspace carving ----
 struct NmsWs {
-  size_t keys_a, keys_b, vals_a, vals_b, sboxes, flags, heads, starts, scalars, rem, cub, total;
+  size_t keys_a, keys_b, vals_a, vals_b, sboxes, flags, heads, starts, scalars, rem, mask, cub, total;
   size_t cub_bytes;
 };
 
@@ -273,6 +423,7 @@ static NmsWs nms_layout(int64_t N) {
   w.starts = take((n + 1) * 4);
   w.scalars = take(64);
   w.rem = take((n / 32 + 2 * (n / 65536) + 8) * 4);     // suppression bits of segments above 65 536 boxes
+  w.mask = take((long long)n <= kMaskMaxN ? n * kMaskWords * 8 : 0);   // IoU bitmask of the few-large-segments path
   // cub temp storage: asked from cub when a device is present, else a documented upper bound
   size_t t1 = 0, t2 = 0, t3 = 0;
   cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, t1, (const unsigned long long*)nullptr,
@@ -361,13 +512,27 @@ static int run_nms(const float* d_boxes, const float* d_scores, const void* d_se
   count_launch(2);
   const int64_t segs = mode == 1 ? (num_segments > 0 ? num_segments : 1) : 1;
   const bool wide = mode == 0 || (n / segs >= 256 && segs < 148 * 4);
+  const long long sweep_topk = mode == 2 ? 0LL : (long long)topk;
+  long long* seg_counts = mode == 1 ? (long long*)d_seg_counts : nullptr;
+  // few large segments (or one segment of at most 2048 boxes): the IoU bitmask is built by the whole grid and every
+  // segment of at most 2048 boxes is resolved by one warp; larger segments of the same call stay with the phased sweep
+  const bool masked = mode != 2 && wide && (long long)n <= kMaskMaxN && (mode == 1 || n <= kMaskMaxSeg);
+  int skip_upto = 0;
+  if (masked) {
+    unsigned long long* mask = (unsigned long long*)(base + w.mask);
+    nms_mask<<<dim3((unsigned)segs, kMaskWords), 256, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, flavor, trash, mask);
+    CPM_CHECK_LAUNCH();
+    nms_sweep_mask<<<(unsigned)segs, 32, 0, st>>>(starts, d_nseg, n, keys_b, sweep_topk, trash, mask, flags, seg_counts,
+                                                  d_total);
+    CPM_CHECK_LAUNCH();
+    skip_upto = kMaskMaxSeg;
+  }
   if (wide)
-    nms_sweep<true><<<mode == 0 ? 1 : 148 * 2, 1024, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr,
-                                                              mode == 2 ? 0LL : (long long)topk, flavor, flags,
-                                                              mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, rem_g, trash);
+    nms_sweep<true><<<mode == 0 ? 1 : 148 * 2, 1024, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, sweep_topk, flavor, flags,
+                                                              seg_counts, d_total, rem_g, trash, skip_upto);
   else
-    nms_sweep<false><<<148 * 4, 256, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, mode == 2 ? 0LL : (long long)topk,
-                                              flavor, flags, mode == 1 ? (long long*)d_seg_counts : nullptr, d_total, rem_g, trash);
+    nms_sweep<false><<<148 * 4, 256, 0, st>>>(sboxes, starts, d_nseg, n, keys_b, thr, sweep_topk, flavor, flags, seg_counts,
+                                              d_total, rem_g, trash, skip_upto);
   CPM_CHECK_LAUNCH();
   if (mode == 2) {
     nms_rekey<<<gb, tb, 0, st>>>(keys_b, vals_b, flags, n, keys_a);
