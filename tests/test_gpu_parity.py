@@ -1105,3 +1105,80 @@ def test_multilevel_pooler_returns_the_input_dtype():
     boxes = [ops.BoxList(synthetic.coco_like_boxes(gen, 12, 64, 96, 8.0, 60.0).cuda(), (96, 64))]
     out = ops.Pooler("ROIAlign", (7, 7), SCALES, 2)(feats, boxes)
     assert out.dtype == torch.float16 and out.shape == (12, 16, 7, 7)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# drop-in under the reference's own model: replay of the recorded op-boundary trace
+# ----------------------------------------------------------------------------------------------------------------
+# tests/golden/dropin_trace.npz = what crossed pet.lib.ops / Pooler / GridPostProcessor.get_boxes while the reference's
+# Generalized_RCNN (published R-50 CPM config, shrunk sizes) ran one training forward + backward and one evaluation pass
+# on CPU with its own kernels (tests/golden/make_dropin_trace.py).  /root/reference cannot travel to the GPU box, so the
+# model is not re-run here: every recorded call is replayed through cpm_r_cnn_b200 with the recorded arguments and
+# compared with what the reference's op returned to the model.
+def _trace_poolers(g, phase, feats):
+    outs = []
+    for i in range(int(g["%s_counts" % phase][0])):
+        key = "%s_pool%d" % (phase, i)
+        ph, pw, sr, aligned, nlev = (int(v) for v in g[key + "_cfg"])
+        scales = [float(s) for s in g[key + "_scales"]]
+        boxes = [ops.BoxList(cuda(g["%s_boxes%d" % (key, j)]), tuple(int(v) for v in g["%s_size%d" % (key, j)]))
+                 for j in range(int(g[key + "_nimg"][0]))]
+        pooler = ops.Pooler("ROIAlignV2" if aligned else "ROIAlign", (ph, pw), scales, sr)
+        out = pooler(feats[:nlev], boxes)
+        close(out.detach().cpu(), g[key + "_out"])
+        outs.append((key, out, (ph, pw), scales, sr, aligned, boxes))
+    return outs
+
+
+def test_dropin_trace_training_iteration(golden):
+    g = golden("dropin_trace")
+    feats = [cuda(g["train_feat%d" % l]).requires_grad_(True) for l in range(4)]       # NCHW, as the FPN hands them over
+    outs = _trace_poolers(g, "train", feats)
+    assert len(outs) == 5 and [o[2] for o in outs] == [(7, 7), (14, 14), (14, 14), (14, 14), (7, 7)]
+    gouts = [cuda(g[key + "_gout"]) for key, *_ in outs]
+    torch.autograd.backward([o[1] for o in outs], gouts)
+    # bound of the summed gradient: the same backward on |grad_out| (red.global.add path), summed over the five poolers
+    shapes = [tuple(f.shape) for f in feats]
+    gabs = [torch.zeros_like(f) for f in feats]
+    for (key, out, size, scales, sr, aligned, boxes), go in zip(outs, gouts):
+        rois = ops.Pooler("ROIAlign", size, scales, sr).convert_to_roi_format(boxes)
+        for a, t in zip(gabs, pooler_backward(go.abs(), shapes, scales, rois, size, sr, bool(aligned), 0, _lib.make_mapper(2, 5),
+                                              mode="atomic")):
+            a += t
+    for l, f in enumerate(feats):
+        assert f.grad.is_contiguous()
+        close_sum(f.grad.cpu(), g["train_gfeat%d" % l], gabs[l].cpu())
+    # the RPN's NMS calls (pet.lib.ops.nms = torchvision.ops.nms on the CPU build that recorded the trace)
+    for i in range(int(g["train_counts"][1])):
+        key = "train_nms%d" % i
+        keep = ops.nms(cuda(g[key + "_boxes"]), cuda(g[key + "_scores"]), float(g[key + "_thr"][0]), iou_flavor=_lib.IOU_PLAIN)
+        assert np.array_equal(keep.cpu().numpy(), g[key + "_keep"])
+    _trace_decodes(g, "train")
+
+
+def _trace_decodes(g, phase):
+    for i in range(int(g["%s_counts" % phase][3])):
+        key = "%s_dec%d" % (phase, i)
+        is_train, stage = (int(v) for v in g[key + "_cfg"])
+        pp = ops.GridPostProcessor(stage, 9, 14)
+        props = ops.BoxList(cuda(g[key + "_boxes"]), tuple(int(v) for v in g[key + "_size"]))
+        out = pp.get_boxes(props, cuda(g[key + "_pred"]), bool(is_train))
+        np.testing.assert_allclose(out.cpu().numpy(), g[key + "_out"], rtol=1e-5, atol=1e-3)
+
+
+def test_dropin_trace_evaluation_pass(golden):
+    g = golden("dropin_trace")
+    feats = [cuda(g["eval_feat%d" % l]) for l in range(4)]
+    with torch.no_grad():
+        outs = _trace_poolers(g, "eval", feats)
+    assert len(outs) == 5
+    for i in range(int(g["eval_counts"][1])):
+        key = "eval_nms%d" % i
+        keep = ops.nms(cuda(g[key + "_boxes"]), cuda(g[key + "_scores"]), float(g[key + "_thr"][0]), iou_flavor=_lib.IOU_PLAIN)
+        assert np.array_equal(keep.cpu().numpy(), g[key + "_keep"])
+    for i in range(int(g["eval_counts"][2])):
+        key = "eval_mlnms%d" % i
+        thr, topk = float(g[key + "_args"][0]), int(g[key + "_args"][1])
+        keep = ops.ml_nms(cuda(g[key + "_boxes"]), cuda(g[key + "_scores"]), cuda(g[key + "_labels"]), thr, topk)
+        assert np.array_equal(keep.cpu().numpy(), g[key + "_keep"])
+    _trace_decodes(g, "eval")

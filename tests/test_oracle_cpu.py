@@ -190,3 +190,27 @@ def test_iou_and_matcher_oracle_match_reference(golden):
     for tag in ("rpn", "head", "grid"):
         hi, lo, allow = g["params_" + tag]
         assert np.array_equal(om.match(g["iou"], hi, lo, bool(allow)), g["match_" + tag])
+
+
+@pytest.mark.parametrize("phase", ["train", "eval"])
+def test_oracle_reproduces_the_model_trace(golden, phase):
+    """The op-boundary trace recorded while the reference's own Generalized_RCNN ran (tests/golden/make_dropin_trace.py):
+    the oracle's level map + per-level RoIAlign reproduce every Pooler output bit for bit, its NMS every keep list --
+    including the levels that received no RoI and the ground-truth boxes the heads append."""
+    g = golden("dropin_trace")
+    feats = [g["%s_feat%d" % (phase, l)] for l in range(4)]
+    for i in range(int(g["%s_counts" % phase][0])):
+        key = "%s_pool%d" % (phase, i)
+        ph, pw, sr, aligned, nlev = (int(v) for v in g[key + "_cfg"])
+        boxes = [g["%s_boxes%d" % (key, j)] for j in range(int(g[key + "_nimg"][0]))]
+        rois = np.concatenate([np.concatenate([np.full((len(b), 1), j, np.float32), b], 1) for j, b in enumerate(boxes)], 0)
+        levels = oracle.level_map(rois, 2, 5)
+        out = np.zeros(g[key + "_out"].shape, np.float32)
+        for l in range(nlev):
+            idx = np.nonzero(levels == l)[0]
+            if len(idx):
+                out[idx] = oracle.roi_align_forward(feats[l], rois[idx], float(g[key + "_scales"][l]), ph, pw, sr, bool(aligned))
+        assert np.array_equal(out, g[key + "_out"])
+    for i in range(int(g["%s_counts" % phase][1])):
+        key = "%s_nms%d" % (phase, i)
+        assert np.array_equal(oracle.nms(g[key + "_boxes"], g[key + "_scores"], float(g[key + "_thr"][0])), g[key + "_keep"])
