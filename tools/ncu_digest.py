@@ -48,7 +48,19 @@ def sass_summary(rep, idx):
             "    stalls     : " + ", ".join("%s %.1f%%" % (k[6:], 100.0 * v / st) for k, v in sc.most_common(7)) + "\n")
 
 
-for rep in sys.argv[1:]:
+# --json PATH: also write {op: dram bytes per launch} for the step's main kernels (what bench.py reports as `traffic`)
+JSON_OUT = None
+ARGS = sys.argv[1:]
+if "--json" in ARGS:
+    i = ARGS.index("--json")
+    JSON_OUT = ARGS[i + 1]
+    ARGS = ARGS[:i] + ARGS[i + 2:]
+DRAM = {}
+OPKEY = (("roi_align_fwd_cols<1", "fwd7"), ("roi_align_fwd_cols<2", "fwd14"), ("bwd_tiles_staged<0, 7, 2>", "bwd7"),
+         ("bwd_tiles_staged<0, 14, 2>", "bwd14"), ("bwd_tiles_staged<0,7,2>", "bwd7"), ("bwd_tiles_staged<0,14,2>", "bwd14"),
+         ("stage_pyramid_f32", "stage"))
+
+for rep in ARGS:
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     if len(rows) < 3:
         continue
@@ -61,6 +73,10 @@ for rep in sys.argv[1:]:
         unit = rows[1][h.index('dram__bytes_read.sum')]
         scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(unit, 1.0)
         print("  [%d] %s  grid %s x block %s" % (n, name, g('launch__grid_size'), g('launch__block_size')))
+        for pat, key in OPKEY:
+            if pat in g("Kernel Name") and key not in DRAM:
+                DRAM[key] = (rd + wr) * scale
+                DRAM[key + "_kernel"] = name
         def mb(key, per=1.0):
             if key not in h or not r[h.index(key)].replace(".", "").replace("e", "").replace("+", "").replace("-", "").isdigit():
                 return float("nan")
@@ -81,3 +97,8 @@ for rep in sys.argv[1:]:
             float(g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed')), float(g('l1tex__t_sector_hit_rate.pct')),
             float(g('lts__t_sector_hit_rate.pct'))))
         sys.stdout.write(sass_summary(rep, n))
+
+if JSON_OUT:
+    import json
+    DRAM["source"] = "ncu --set full --clock-control none, one capture per kernel of tools/profile_step.py (per launch): " + ", ".join(a.split("/")[-1] for a in ARGS)
+    json.dump(DRAM, open(JSON_OUT, "w"), indent=1)

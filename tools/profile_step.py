@@ -1,7 +1,14 @@
-"""One warm-up-then-measure pass of the bench step (7x7 + 14x14 Pooler fwd+bwd on the configs[1] workload) for ncu.
-    python tools/profile_step.py [--steps N] [--nms]
+"""The bench step for profilers and quick timing.
+
+    python tools/profile_step.py [--steps N] [--graph] [--resident] [--nms]
+
+Default: the headline step of bench.py -- NCHW maps in, one NHWC staging of the pyramid, 7x7 and 14x14 Pooler forward +
+deterministic backward writing NCHW gradients -- run eagerly `--steps` times (what ncu attaches to).  --resident: the four
+ops on a pyramid that is already channels_last (NHWC gradients), the round-1 configuration.  --graph: per-op CUDA-graph
+replay times (median) instead of eager runs.
 """
 import argparse
+import importlib
 import os
 import sys
 
@@ -14,67 +21,72 @@ from cpm_r_cnn_b200 import _lib, synthetic as sy  # noqa: E402
 from cpm_r_cnn_b200.roi_align import pooler_backward, pooler_forward  # noqa: E402
 import cpm_r_cnn_b200 as ops  # noqa: E402
 
+ra = importlib.import_module("cpm_r_cnn_b200.roi_align")
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--nms", action="store_true")
 ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (no host enqueue cost in the numbers)")
+ap.add_argument("--resident", action="store_true", help="channels_last pyramid, NHWC gradients (round-1 configuration)")
 ap.add_argument("--mode", default="deterministic")
-ap.add_argument("--impl", type=int, default=0)
-ap.add_argument("--cl", action="store_true", help="channels_last pooled tensors (forward output and grad_out)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 rois_h, feats_h, gouts_h = bench.make_workload(0)
-feats = [f.to(dev).contiguous(memory_format=torch.channels_last) for f in feats_h]
+feats = [f.to(dev) for f in feats_h]
+if args.resident:
+    feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
 rois = rois_h.to(dev)
 gouts = [g.to(dev) for g in gouts_h]
-if args.cl:
-    gouts = [g.contiguous(memory_format=torch.channels_last) for g in gouts]
 shapes = [tuple(f.shape) for f in feats_h]
+scales = list(sy.FPN_SCALES)
 mapper = _lib.make_mapper(2, 5)
+nchw = not args.resident
+names, fns = [], []
+if nchw:
+    names.append("stage")
+    fns.append(lambda: ra.stage_pyramid_nhwc(feats, cache=True))
+for p, go in zip(bench.POOLERS, gouts):
+    names += ["fwd%d" % p[0], "bwd%d" % p[0]]
+    fns.append(lambda p=p: pooler_forward(feats, scales, rois, p, 2, False, 0, mapper))
+    fns.append(lambda p=p, go=go: pooler_backward(go, shapes, scales, rois, p, 2, False, 0, mapper, mode=args.mode, nchw_grad=nchw))
+
+
+def run_step():
+    ra.STAGING_CACHE.clear()
+    return [f() for f in fns]
+
+
 tot = {}
 if args.graph:
-    ops_ = []
-    for p, go in zip(bench.POOLERS, gouts):
-        ops_.append(lambda p=p: pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl, channels_last=args.cl))
-        ops_.append(lambda p=p, go=go: pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode))
-    for f in ops_:
-        f(); f()
+    for _ in range(2):
+        run_step()
     torch.cuda.synchronize()
-    graphs, keep = [], []
-    for f in ops_:
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            keep.append(f())
-        graphs.append(g)
-    for i in range(args.steps + 3):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        for j, g in enumerate(graphs):
-            evs[j].record(); g.replay()
-        evs[4].record()
+    ra.STAGING_CACHE.clear()
+    caps = [bench.capture(f) for f in fns]          # the staging graph fills the cache the forward graphs then hit
+    for n, t in zip(names, bench.time_graphs([c[0] for c in caps], max(args.steps, 5))):
+        tot[n] = [t]
+else:
+    for i in range(args.steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)]
+        ra.STAGING_CACHE.clear()
+        for j, f in enumerate(fns):
+            evs[j].record()
+            f()
+        evs[len(fns)].record()
         torch.cuda.synchronize()
-        if i >= 3:
-            for j, n in enumerate(["fwd7", "bwd7", "fwd14", "bwd14"]):
+        if i >= 2:
+            for j, n in enumerate(names):
                 tot.setdefault(n, []).append(evs[j].elapsed_time(evs[j + 1]))
-    args.steps = 0
-for i in range(args.steps):
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    k = 0
-    for p, go in zip(bench.POOLERS, gouts):
-        evs[k].record()
-        out = pooler_forward(feats, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, impl=args.impl, channels_last=args.cl)
-        evs[k + 1].record()
-        grads = pooler_backward(go, shapes, list(sy.FPN_SCALES), rois, p, 2, False, 0, mapper, mode=args.mode)
-        k += 2
-    evs[k].record()
-    torch.cuda.synchronize()
-    if i >= 2:
-        for j, n in enumerate(["fwd7", "bwd7", "fwd14", "bwd14"]):
-            tot.setdefault(n, []).append(evs[j].elapsed_time(evs[j + 1]))
 if tot:
     ab = bench.algorithmic_bytes(rois_h)
+    total = 0.0
     for n, v in tot.items():
         ms = sorted(v)[len(v) // 2]
-        print("%-6s median %.4f ms  min %.4f ms   %.0f GB/s  frac %.3f" % (n, ms, min(v), ab[n] / ms / 1e6, ab[n] / ms / 1e6 / 6540.8))
+        total += ms
+        if n in ab:
+            print("%-6s median %.4f ms  min %.4f ms   %.0f GB/s  frac %.3f" % (n, ms, min(v), ab[n] / ms / 1e6, ab[n] / ms / 1e6 / 6540.8))
+        else:
+            print("%-6s median %.4f ms  min %.4f ms" % (n, ms, min(v)))
+    print("step   %.4f ms" % total)
 if args.nms:
     gen = torch.Generator().manual_seed(1000)
     b, s, seg = sy.rpn_like_candidates(gen, 16, 5, 1000)
