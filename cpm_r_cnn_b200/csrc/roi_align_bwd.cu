@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_red(PyramidView pv, co
 constexpr int TH = 8, TW = 8;          // tile: 8 rows (one per warp) x 8 columns (register-unrolled)
 constexpr int kTileThreads = 256;
 constexpr int kMaxP = 32;              // pooled size limit of this path (bin ranges are 32-bit ballots)
+constexpr int kCandCap = 64;           // prepared candidates per 8x8 tile; a busier tile is scanned by its CTAs
 
 // workspace layout: int32 seg_count[L*B] ; int32 perm[L*B][K]
 __device__ __forceinline__ void bin_rois_block(const PyramidView& pv, const float* __restrict__ rois, int K, const MapperView& mp,
@@ -221,7 +222,12 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
                                                int aligned, const MapperView& mp, const int* __restrict__ roi_levels,
                                                TapS* __restrict__ taps, int4* __restrict__ box, const int r, const int tid,
                                                int* __restrict__ segid, int* __restrict__ rowclip, const int NBy,
-                                               int* __restrict__ colclip, const int NBx) {
+                                               int* __restrict__ colclip, const int NBx, const TileGrid& tg8,
+                                               int* __restrict__ tile_count, int2* __restrict__ cands) {
+  // per group of 64 threads: the axis clips of the RoI's bands, exchanged between its two warps for the tile lists
+  __shared__ int s_clip[4][2][64];
+  __shared__ int s_b0[4][2], s_nb[4][2];
+  const int grp = (threadIdx.x >> 6) & 3;
   const float* roi = rois + 5 * (long)r;
   const int l = roi_level_b(roi, pv, mp, roi_levels, r);
   const int nt = (PH + PW) * G;
@@ -239,6 +245,7 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
     }
     return;
   }
+  if (ln == 0) s_nb[grp][isx] = 0;
   const int H = pv.H[l], W = pv.W[l];
   const RoiGeo<float> g = roi_geometry<float>(roi, pv.scale[l], PH, PW, G, aligned != 0);
   const int P = isx ? PW : PH;
@@ -266,9 +273,36 @@ __device__ __forceinline__ void roi_taps_group(const PyramidView& pv, const floa
     if (valid) {
       const int lo0 = __shfl_sync(0xffffffffu, mine.lo, __ffs(valid) - 1);
       const int hi1 = __shfl_sync(0xffffffffu, mine.hi, 31 - __clz(valid));
-      for (int b = lo0 >> 3; b <= (hi1 >> 3) && b < NB; b++) {
+      const int b0 = lo0 >> 3;
+      for (int b = b0; b <= (hi1 >> 3) && b < NB; b++) {
         const unsigned m = __ballot_sync(0xffffffffu, v && mine.hi >= 8 * b && mine.lo < 8 * b + 8);
-        if (ln == 0 && m) clip[(long)r * NB + b] = ((__ffs(m) - 1) / G) | (((31 - __clz(m)) / G) << 8);
+        const int cv = m ? ((__ffs(m) - 1) / G) | (((31 - __clz(m)) / G) << 8) : 1;
+        if (ln == 0) {
+          if (m) clip[(long)r * NB + b] = cv;
+          if (b - b0 < 64) s_clip[grp][isx][b - b0] = cv;
+        }
+      }
+      if (ln == 0) {
+        s_b0[grp][isx] = b0;
+        s_nb[grp][isx] = min(min(hi1 >> 3, NB - 1) - b0 + 1, 64);
+      }
+    }
+  }
+  if (tile_count != nullptr) {
+    // ---- the RoI appends itself to the candidate list of every 8x8 tile it has taps in: {RoI, clipped bin ranges}.
+    //      The order inside a list is that of the atomics; the tile kernel sorts its (<= kCandCap) entries by RoI ----
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+    const int nby = s_nb[grp][0], nbx = s_nb[grp][1];
+    const int tiles_x = tg8.tiles_x[l], per_img = tiles_x * tg8.tiles_y[l];
+    const int tbase = tg8.first[pv.num_levels - 1 - l] + (int)roi[0] * per_img;
+    for (int e = tid; e < nby * nbx; e += 64) {
+      const int iy = e / nbx, ix = e - iy * nbx;
+      const int rc = s_clip[grp][0][iy], cc = s_clip[grp][1][ix];
+      if ((rc & 255) <= (rc >> 8) && (cc & 255) <= (cc >> 8)) {
+        const int t = tbase + (s_b0[grp][0] + iy) * tiles_x + s_b0[grp][1] + ix;
+        const int pos = atomicAdd(tile_count + t, 1);
+        if (pos < kCandCap)
+          cands[(long)t * kCandCap + pos] = make_int2(r, (rc & 255) | ((rc >> 8) << 8) | ((cc & 255) << 16) | ((cc >> 8) << 24));
       }
     }
   }
@@ -292,7 +326,8 @@ __global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* 
                                                     int aligned, MapperView mp, const int* __restrict__ roi_levels,
                                                     int* __restrict__ seg_count, int* __restrict__ perm,
                                                     TapS* __restrict__ taps, int4* __restrict__ box, int* __restrict__ segid,
-                                                    int* __restrict__ rowclip, int NBy, int* __restrict__ colclip, int NBx) {
+                                                    int* __restrict__ rowclip, int NBy, int* __restrict__ colclip, int NBx,
+                                                    TileGrid tg8, int* __restrict__ tile_count, int2* __restrict__ cands) {
   const int nseg = pv.num_levels * pv.batch;
   if ((int)blockIdx.x < nseg) {
     bin_rois_block(pv, rois, K, mp, roi_levels, seg_count, perm, blockIdx.x);
@@ -300,57 +335,8 @@ __global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* 
     const int r = 4 * ((int)blockIdx.x - nseg) + (threadIdx.x >> 6);
     if (r < K)
       roi_taps_group(pv, rois, PH, PW, G, aligned, mp, roi_levels, taps, box, r, threadIdx.x & 63, segid, rowclip, NBy, colclip,
-                     NBx);
+                     NBx, tg8, tile_count, cands);
   }
-}
-
-// Per 8x8-pixel tile (one warp each, launch order of the tile kernel): the RoIs that reach the tile, in RoI order, with
-// the bin rows / columns that have a sample tap inside it -- what a tile CTA would otherwise find by scanning its
-// (level, image) list and reading every candidate's taps.  At most kCandCap entries are stored; a busier tile (count >
-// kCandCap) is scanned by its CTAs as before.
-constexpr int kCandCap = 64;
-
-__global__ void __launch_bounds__(256) bwd_tile_cands(PyramidView pv, TileGrid tg, int K, const int4* __restrict__ box,
-                                                       const int* __restrict__ segid, const int* __restrict__ rowclip, int NBy,
-                                                       const int* __restrict__ colclip, int NBx, int* __restrict__ tile_count,
-                                                       int2* __restrict__ cands, int ntiles) {
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (t >= ntiles) return;
-  const TileId id = decode_tile(tg, pv.num_levels, t, 8, 8);
-  const int seg = id.l * pv.batch + id.b;
-  const int by = id.y0 >> 3, bx = id.x0 >> 3;
-  int2* out = cands + (long)t * kCandCap;
-  int cnt = 0;
-  for (int base = 0; base < K; base += 128) {
-    int sg[4];
-    int4 bxv[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int r = base + 32 * u + lane;
-      sg[u] = r < K ? __ldg(segid + r) : -1;
-      bxv[u] = r < K ? __ldg(box + r) : make_int4(1, 0, 1, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (base + 32 * u >= K) break;
-      const int r = base + 32 * u + lane;
-      const int4 b4 = bxv[u];
-      bool hit = sg[u] == seg && b4.x <= b4.y && b4.x < id.y0 + 8 && b4.y >= id.y0 && b4.z < id.x0 + 8 && b4.w >= id.x0;
-      int cr = 0;
-      if (hit) {
-        const int rc = by < NBy ? __ldg(rowclip + (long)r * NBy + by) : 1;
-        const int cc = bx < NBx ? __ldg(colclip + (long)r * NBx + bx) : 1;
-        hit = (rc & 255) <= (rc >> 8) && (cc & 255) <= (cc >> 8);
-        cr = (rc & 255) | ((rc >> 8) << 8) | ((cc & 255) << 16) | ((cc >> 8) << 24);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      const int pos = cnt + __popc(bal & ((1u << lane) - 1));
-      if (hit && pos < kCandCap) out[pos] = make_int2(r, cr);
-      cnt += __popc(bal);
-    }
-  }
-  if (lane == 0) tile_count[t] = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -462,7 +448,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
 #pragma unroll
   for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
 
-  // the tile's candidates: prepared by bwd_tile_cands (RoI + clipped bin ranges; one load), or -- a tile busier than the
+  // the tile's candidates: appended by bwd_prepare (RoI + clipped bin ranges; one load + a rank sort), or -- a tile busier than the
   // prepared list holds, or a call without the lists -- found by scanning the (level, image) RoI list
   const int pc = tile_count ? tile_count[tile_id] : -1;
   const bool prepared = pc >= 0 && pc <= kCandCap;
@@ -481,10 +467,19 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
   for (int base = 0; base < nseg; base += kRound) {
     int ncand = 0;
     if (prepared) {
+      // the list was appended to with atomics: ranking the (distinct) RoI indices restores RoI order = the summation order
+      int2 e = make_int2(0, 0);
+      int* scratch = &sm.cand[kRound - kCandCap];              // the tail of the candidate array (ranks stay below it)
       if ((int)threadIdx.x < pc) {
-        const int2 e = __ldg(cands + (long)tile_id * kCandCap + threadIdx.x);
-        sm.cand[threadIdx.x] = e.x;
-        sm.crange[threadIdx.x] = e.y;
+        e = cands[(long)tile_id * kCandCap + threadIdx.x];
+        scratch[threadIdx.x] = e.x;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < pc) {
+        int rank = 0;
+        for (int i = 0; i < pc; i++) rank += scratch[i] < e.x;
+        sm.cand[rank] = e.x;
+        sm.crange[rank] = e.y;
       }
       ncand = pc;
       __syncthreads();
@@ -908,10 +903,15 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
     int4* box = (int4*)(wsb + w.box);
     const int Kp = K > 0 ? (int)K : 1;
     if (K > 0) {
+      TileGrid tg8;
+      const long tiles8 = make_tile_grid(tg8, grad_feat, TH, TW);
+      const bool lists = !tma && w.NBy > 0 && w.NBy <= 64 && w.NBx <= 64;
+      if (lists) CPM_CHECK_CUDA(cudaMemsetAsync(wsb + w.tile_count, 0, (size_t)tiles8 * sizeof(int), st));
       bwd_prepare<<<(unsigned)(L * B + (K + 3) / 4), 256, 0, st>>>(
           pv, (const float*)d_rois, (int)K, pooled_h, pooled_w, sampling_ratio, aligned, mp, d_roi_levels, seg_count, perm, taps,
           box, w.NBy ? (int*)(wsb + w.segid) : nullptr, w.NBy ? (int*)(wsb + w.rowclip) : nullptr, w.NBy,
-          w.NBx ? (int*)(wsb + w.colclip) : nullptr, w.NBx);
+          w.NBx ? (int*)(wsb + w.colclip) : nullptr, w.NBx, tg8, lists ? (int*)(wsb + w.tile_count) : nullptr,
+          lists ? (int2*)(wsb + w.cands) : nullptr);
       CPM_CHECK_LAUNCH();
     } else {
       CPM_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, (size_t)L * B * sizeof(int), st));
@@ -942,14 +942,7 @@ extern "C" int cpm_roi_align_backward_ex(const cpm_pyramid_t* grad_feat, const v
         }
       }
     }
-    const bool lists = w.NBy > 0 && K > 0;
-    if (lists) {
-      bwd_tile_cands<<<(unsigned)((tiles + 7) / 8), 256, 0, st>>>(pv, tg, (int)K, box, (const int*)(wsb + w.segid),
-                                                                 (const int*)(wsb + w.rowclip), w.NBy,
-                                                                 (const int*)(wsb + w.colclip), w.NBx,
-                                                                 (int*)(wsb + w.tile_count), (int2*)(wsb + w.cands), (int)tiles);
-      CPM_CHECK_LAUNCH();
-    }
+    const bool lists = w.NBy > 0 && w.NBy <= 64 && w.NBx <= 64 && K > 0;
     fn<<<(unsigned)(tiles * chunks), kTileThreads, sizeof(bst::Smem), st>>>(
         pv, tg, (const float*)d_grad_out, taps, box, Kp, pooled_h, pooled_w, sampling_ratio, seg_count, perm, chunks,
         lists ? (const int*)(wsb + w.tile_count) : nullptr, lists ? (const int2*)(wsb + w.cands) : nullptr);
