@@ -132,6 +132,7 @@ def cpu_reference_rate(sample_rois_per_img=48):
     """The reference's CPU RoIAlign through the reference Pooler's per-level loop (poolers.py:127-130), forward +
     backward at 7x7 and 14x14, on the first `sample_rois_per_img` RoIs of each image of the rank-0 workload."""
     from cpm_r_cnn_b200 import synthetic as sy
+    prev_threads = torch.get_num_threads()
     torch.set_num_threads(1)      # the kernel is single-threaded by construction (ROIAlign_cpu.cpp:185-186: omp commented out)
     if 0 not in _WORKLOAD_CACHE:
         _WORKLOAD_CACHE[0] = make_workload(0)
@@ -164,6 +165,7 @@ def cpu_reference_rate(sample_rois_per_img=48):
             assert o.shape[0] == r.shape[0] and g.shape == f.shape
         units += rois.shape[0]
     dt = time.perf_counter() - t0
+    torch.set_num_threads(prev_threads)
     sample = ("%d of %d RoIs/img x %d img, 7x7 + 14x14 fwd+bwd through the per-level Pooler loop, fp32, 4 levels x %d ch"
               % (sample_rois_per_img, ROIS_PER_IMG, IMGS_PER_GPU, CHANNELS))
     return units / dt, dt, kind, sample
@@ -203,6 +205,14 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """CPU threads this process may use (its affinity mask, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def bind_to_gpu_cores(index):
     """Pins this process to the CPU cores NVML reports as local to GPU `index` (before any pinned allocation, so that the
     staging buffers are first-touched on that NUMA node).  Returns a short description for the JSON line."""
@@ -333,6 +343,7 @@ def bench_config0(dev):
     try:
         from oracle import build_ref
         ref = build_ref.load("pet_ref_cpu")
+        prev_threads = torch.get_num_threads()
         torch.set_num_threads(1)
         t0 = time.perf_counter()
         out = torch.zeros((512, CHANNELS, 7, 7))
@@ -345,17 +356,20 @@ def bench_config0(dev):
                                 "max_abs_diff_vs_gpu": float((out - out_gpu).abs().max()),
                                 "within_1e-5_rel": bool(((out - out_gpu).abs() <= 1e-5 * (out.abs() + rms)).all())}
         res["speedup_vs_reference_cpu"] = dt * 1e3 / ms
+        torch.set_num_threads(prev_threads)
     except Exception as ex:
         res["reference_cpu"] = {"unavailable": repr(ex)[:200]}
     try:
         import torchvision
-        torch.set_num_threads(os.cpu_count() or 1)
+        prev_threads = torch.get_num_threads()
+        torch.set_num_threads(host_threads())
         t0 = time.perf_counter()
         for l, f in enumerate(feats):
             idx = torch.nonzero(lv == l).squeeze(1)
             torchvision.ops.roi_align(f, rois[idx].contiguous(), (7, 7), scales[l], SAMPLING, False)
         dt = time.perf_counter() - t0
         res["torchvision_cpu"] = {"ms": dt * 1e3, "rois_per_sec": 512 / dt, "cores": torch.get_num_threads()}
+        torch.set_num_threads(prev_threads)
     except Exception as ex:
         res["torchvision_cpu"] = {"unavailable": repr(ex)[:200]}
     return res
@@ -375,6 +389,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the cpm_ops path has no CPU fallback")
     affinity = bind_to_gpu_cores(local)       # before CUDA / pinned allocations: NUMA-local staging buffers
+    torch.set_num_threads(host_threads())     # torch's intra-op pool follows the affinity mask, not the machine's core count
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # stdout carries exactly one line, the JSON: everything libraries print while the job runs (NCCL writes its version
@@ -798,7 +813,8 @@ def cpu_nms_baseline(name, b, s, seg, nseg, thr, ours_keep):
         order = torch.argsort(sg, stable=True)
         counts = torch.bincount(sg, minlength=nseg).tolist()
         bs, ss, gs = bc[order].contiguous(), sc[order].contiguous(), sg[order].contiguous()
-        torch.set_num_threads(os.cpu_count() or 1)
+        prev_threads = torch.get_num_threads()
+        torch.set_num_threads(host_threads())
         t0 = time.perf_counter()
         kept, pos = [], 0
         if name.startswith("rpn"):
@@ -816,8 +832,10 @@ def cpu_nms_baseline(name, b, s, seg, nseg, thr, ours_keep):
                 pos += c
             op = "torchvision.ops.batched_nms (CPU) per image"
         dt = time.perf_counter() - t0
+        cores = torch.get_num_threads()
+        torch.set_num_threads(prev_threads)
         kept = torch.cat(kept) if kept else torch.empty(0, dtype=torch.int64)
-        out = {"op": op, "ms": dt * 1e3, "boxes_per_sec": b.shape[0] / dt, "cores": torch.get_num_threads(), "kind": "torchvision",
+        out = {"op": op, "ms": dt * 1e3, "boxes_per_sec": b.shape[0] / dt, "cores": cores, "kind": "torchvision",
                "same_keep_set_as_ours": bool(torch.equal(torch.sort(kept)[0], torch.sort(ours_keep.cpu())[0]))}
     except Exception as e:
         out = {"unavailable": repr(e)[:200]}

@@ -43,11 +43,12 @@ class CLSPostProcessor(nn.Module):
         counts = [len(b) for b in boxes]
         B = len(boxes)
         concat = torch.cat([b.bbox for b in boxes], dim=0).float()
-        img_of_box = torch.repeat_interleave(torch.arange(B, device=dev), torch.tensor(counts, device=dev))
+        # per-box image index and clip limits are functions of the (host-known) box counts: built on the host, one upload
+        img_host = torch.repeat_interleave(torch.arange(B), torch.tensor(counts))
+        lim_host = torch.tensor([[w - 1.0, h - 1.0, w - 1.0, h - 1.0] for (w, h) in image_shapes], dtype=torch.float32)[img_host]
+        img_of_box = img_host.to(dev, non_blocking=True)
         # clip_to_image(remove_empty=False), bounding_box.py:294-299, for every image at once
-        lim = torch.tensor([[w - 1.0, h - 1.0, w - 1.0, h - 1.0] for (w, h) in image_shapes], dtype=torch.float32,
-                           device=dev)[img_of_box]
-        concat = torch.minimum(concat.clamp(min=0), lim)
+        concat = torch.minimum(concat.clamp(min=0), lim_host.to(dev, non_blocking=True))
         # filter_results (:107-124): score > thresh and label != 0, labels = column index
         mask = class_prob > self.score_thresh
         mask[:, 0] = False
@@ -56,27 +57,32 @@ class CLSPostProcessor(nn.Module):
         cand_scores = class_prob[nz[:, 0], nz[:, 1]]
         cand_labels = nz[:, 1]
         cand_img = img_of_box[nz[:, 0]]
-        results = []
         if self.nms <= 0:                                     # boxlist_ml_nms returns its input (boxlist_ops.py:58-59)
-            keep_sorted, kept_img = torch.arange(nz.shape[0], device=dev), cand_img
+            keep_sorted = torch.arange(nz.shape[0], device=dev)
+            per_img = torch.bincount(cand_img, minlength=B).tolist()
         else:
             seg = (cand_img * num_classes + cand_labels).to(torch.int32)
-            keep, _ = batched_nms(cand_boxes, cand_scores, seg, B * num_classes, self.nms, 0,
-                                  iou_flavor=_lib.IOU_ML_CUDA, return_counts=True)
-            # ml_nms returns every image's survivors by decreasing score over all labels (ml_nms.cu:92-94,143-145):
-            # order by (image, -score), ties by candidate index
+            keep_buf, seg_counts, total = batched_nms(cand_boxes, cand_scores, seg, B * num_classes, self.nms, 0,
+                                                      iou_flavor=_lib.IOU_ML_CUDA, sync=False)
+            # the one host round trip after the candidate count: survivors in total and per image
+            sizes = torch.cat([total.reshape(1), seg_counts.reshape(B, num_classes).sum(1)]).tolist()
+            keep = keep_buf[:sizes[0]]
+            per_img = sizes[1:]
+            # ml_nms returns every image's survivors by decreasing score over all labels (ml_nms.cu:92-94,143-145): order by
+            # (image, -score), ties by candidate index.  `keep` is grouped by (image, class) segment, i.e. by image already.
             keep = keep.sort().values
             order = torch.argsort(cand_scores[keep], descending=True, stable=True)
             keep = keep[order]
             keep_sorted = keep[torch.argsort(cand_img[keep], stable=True)]
-            kept_img = cand_img[keep_sorted]
-        per_img = torch.bincount(kept_img, minlength=B).tolist()
+        # one gather per field for the whole batch; the per-image BoxLists are views of it
+        all_boxes, all_scores, all_labels = cand_boxes[keep_sorted], cand_scores[keep_sorted], cand_labels[keep_sorted]
+        results = []
         pos = 0
         for i in range(B):
-            idx = keep_sorted[pos:pos + per_img[i]]
-            pos += per_img[i]
-            bl = BoxList(cand_boxes[idx], image_shapes[i], mode="xyxy")
-            bl.add_field("scores", cand_scores[idx])
-            bl.add_field("labels", cand_labels[idx])
+            n = int(per_img[i])
+            bl = BoxList(all_boxes[pos:pos + n], image_shapes[i], mode="xyxy")
+            bl.add_field("scores", all_scores[pos:pos + n])
+            bl.add_field("labels", all_labels[pos:pos + n])
             results.append(bl)
+            pos += n
         return results
