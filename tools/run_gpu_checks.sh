@@ -13,12 +13,12 @@ if [ "$mode" != "quick" ]; then
   tail -n 2 gpurun_out/smoke.log
 fi
 if [ "$mode" = "profile" ]; then
-  # launch list of one step (step 3 of 3: 9 launches = stage, fwd7, prepare, cands, bwd7, fwd14, prepare, cands, bwd14), then
+  # launch list of one step (step 3 of 3: 7 launches = stage, fwd7, prepare, bwd7, fwd14, prepare, bwd14), then
   # one `--set full` capture per kernel of that step; each only after the same command has exited 0 without ncu
   python tools/profile_step.py --steps 3 > gpurun_out/plain2.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,l1tex__t_bytes.sum,smsp__inst_executed.sum \
-      --clock-control none -s 18 -c 9 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py --steps 3 > gpurun_out/ncu_list.log 2>&1
-  ncu --set full --import-source on --clock-control none -s 18 -c 9 -o gpurun_out/prof_step -f python tools/profile_step.py --steps 3 > gpurun_out/ncu_full.log 2>&1
+      --clock-control none -s 14 -c 7 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py --steps 3 > gpurun_out/ncu_list.log 2>&1
+  ncu --set full --import-source on --clock-control none -s 14 -c 7 -o gpurun_out/prof_step -f python tools/profile_step.py --steps 3 > gpurun_out/ncu_full.log 2>&1
   python tools/profile_step.py --steps 1 --nms > /dev/null 2>&1 && \
   ncu --set full --clock-control none -k regex:'nms_mask|nms_sweep' -c 6 -o gpurun_out/prof_nms -f python tools/profile_step.py --steps 1 --nms > gpurun_out/ncu_nms.log 2>&1
   ls -la gpurun_out/*.ncu-rep
