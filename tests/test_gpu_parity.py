@@ -1182,3 +1182,45 @@ def test_dropin_trace_evaluation_pass(golden):
         keep = ops.ml_nms(cuda(g[key + "_boxes"]), cuda(g[key + "_scores"]), cuda(g[key + "_labels"]), thr, topk)
         assert np.array_equal(keep.cpu().numpy(), g[key + "_keep"])
     _trace_decodes(g, "eval")
+
+
+def test_level2_C_module_against_the_reference_build():
+    """INTEGRATION.md level 2: cpm_r_cnn_b200.compat_C carries the `_C` names and positional signatures the reference's
+    Python calls (roi_align.py:24,46; nms.py:11).  Driven exactly as the reference's per-level Pooler loop drives `_C` --
+    one call per level, NCHW maps in, NCHW gradients out, empty levels included -- and compared with the reference's own
+    CUDA build of the same functions (bound: as test_live_reference_cuda_roi_align)."""
+    from cpm_r_cnn_b200 import compat_C as C
+    ref = _ref_cuda()
+    g = torch.Generator().manual_seed(77)
+    B, Cc = 2, 64
+    feats = synthetic.pyramid(g, B, Cc, 200, 336)
+    rois = synthetic.coco_like_rois(g, 40, B, 200, 336)
+    lv = oracle.level_map(rois.numpy(), 2, 5)
+    for P in (7, 14):
+        for l, fh in enumerate(feats):
+            f = fh.cuda()
+            sel = lv == l
+            r = rois[torch.as_tensor(sel)].cuda().contiguous()
+            _, _, H, W = f.shape
+            mine = C.roi_align_forward(f, r, SCALES[l], P, P, 2, False, 0)
+            want = ref.roi_align_forward(f, r, SCALES[l], P, P, 2, False, 0)
+            assert mine.shape == want.shape and mine.dtype == want.dtype and mine.is_contiguous()
+            cpu = oracle.roi_align_forward(fh.numpy(), rois.numpy()[sel], SCALES[l], P, P, 2, False)
+            ro = want.cpu().numpy().astype(np.float64)
+            rms = float(np.sqrt(np.mean(ro ** 2))) if ro.size else 0.0
+            assert np.all(np.abs(mine.cpu().numpy() - ro) <= np.abs(cpu - ro) + 1e-5 * (np.abs(ro) + rms))
+            go = torch.randn(want.shape, generator=g).cuda()
+            gm = C.roi_align_backward(go, r, SCALES[l], P, P, B, Cc, H, W, 2, False, 0)
+            gw = ref.roi_align_backward(go, r, SCALES[l], P, P, B, Cc, H, W, 2, False, 0).cpu().numpy().astype(np.float64)
+            ga = ref.roi_align_backward(go.abs(), r, SCALES[l], P, P, B, Cc, H, W, 2, False, 0).cpu().numpy()
+            gcpu = oracle.roi_align_backward(go.cpu().numpy(), rois.numpy()[sel], SCALES[l], P, P, B, Cc, H, W, 2, False)
+            assert gm.shape == gw.shape and gm.is_contiguous()
+            grms = float(np.sqrt(np.mean(gw ** 2)))
+            assert np.all(np.abs(gm.cpu().numpy() - gw) <= np.abs(gcpu - gw) + 1e-5 * (ga + grms))
+            # deterministic: a second call returns the same bits (the reference's atomicAdd backward does not)
+            assert torch.equal(gm, C.roi_align_backward(go, r, SCALES[l], P, P, B, Cc, H, W, 2, False, 0))
+    empty = C.roi_align_forward(feats[0].cuda(), rois[:0].cuda(), 0.25, 7, 7, 2, False, 0)
+    assert empty.shape == (0, Cc, 7, 7)
+    boxes, scores, segs, labels, img = synthetic.detection_candidates(g, 1, 300, 80)
+    assert torch.equal(C.ml_nms(boxes.cuda(), scores.cuda(), labels.cuda(), 0.3, 0),
+                       ref.ml_nms(boxes.cuda(), scores.cuda(), labels.cuda(), 0.3, 0))
