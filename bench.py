@@ -398,8 +398,10 @@ def run_ours(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")
     _lib.lib()
     skip = os.environ.get("CPM_BENCH_SKIP", "")
 
@@ -417,7 +419,11 @@ def run_ours(args):
     names = ["fwd7", "bwd7", "fwd14", "bwd14"]
 
     def sync_all():
+        # Ranks that arrive early wait on the HOST (gloo) first, so that the NCCL barrier kernel never sits spinning on a
+        # GPU while rank 0 is still running one of its rank-0-only arms: a pending NCCL kernel on the peer was measured to
+        # slow rank 0's host-synchronising arms 14x (detection post-process 0.98 -> 14 ms at N = 2).
         if world > 1:
+            dist.barrier(group=host_group)
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -757,7 +763,7 @@ def run_ours(args):
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
-        dist.barrier()
+        sync_all()
         dist.destroy_process_group()
 
 
