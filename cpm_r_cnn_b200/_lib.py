@@ -15,7 +15,7 @@ NCHW, NHWC = 0, 1
 INTERP = {"bilinear": 0, "nearest": 1}
 IOU_PLAIN, IOU_TV_CUDA, IOU_ML_CUDA = 0, 1, 2
 BWD_DETERMINISTIC, BWD_ATOMIC = 0, 1
-FWD_AUTO, FWD_GENERIC, FWD_NHWC, FWD_COLS = 0, 1, 2, 4
+FWD_AUTO, FWD_GENERIC, FWD_NHWC, FWD_COLS, FWD_ROWS = 0, 1, 2, 4, 8
 POOLED_KCHW, POOLED_KHWC = 0, 1
 ERR_UNSUPPORTED = -2
 

@@ -16,14 +16,14 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcpm_ops.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_bwd.cu", "roi_align_bwd_tma.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "matcher.cu", "layout.cu"]
+SOURCES = ["api.cu", "roi_align_fwd.cu", "roi_align_fwd_cols.cu", "roi_align_fwd_rows.cu", "roi_align_bwd.cu", "roi_align_bwd_tma.cu", "nms.cu", "grid_decode.cu", "rpn_decode.cu", "grid_targets.cu", "matcher.cu", "layout.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "roi_align_bwd.cuh"), os.path.join(INCLUDE, "cpm_ops.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: no implicit contraction -- every fused multiply-add in the kernels is an explicit fmaf(), which is what
 # lets the arithmetic be pinned against the reference (see DESIGN.md "Numerics").
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE, "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE, "--expt-relaxed-constexpr"] + os.environ.get("CPM_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):

@@ -15,6 +15,9 @@
 //   The FPN level of each RoI (LevelMapper, poolers.py:29-40) is evaluated inside every kernel.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cpm {
@@ -273,6 +276,23 @@ bool fwd_cols_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
 int launch_fwd_cols(const PyramidView& pv, const float* rois, long K, int P, int G, int aligned, const MapperView& mp,
                     const int* lv, void* out, int out_channels_last, cudaStream_t st);
 
+bool fwd_rows_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, int sampling_ratio, const void* d_out);
+int launch_fwd_rows(const cpm_pyramid_t* feat, const PyramidView& pv, const float* rois, long K, int P, int G, int aligned,
+                    const MapperView& mp, const int* lv, float* out, cudaStream_t st);
+
+// CPM_FWD_IMPL=rows|cols forces one of the two kernels of the CPM poolers for calls that leave the choice to the library
+// (default: the row-streaming kernel where it applies -- fp32, (K,C,PH,PW) output -- else the column-table kernel)
+static int fwd_impl_env() {
+  static const int v = [] {
+    const char* e = getenv("CPM_FWD_IMPL");
+    if (e == nullptr) return 0;
+    if (strcmp(e, "rows") == 0) return CPM_FWD_ROWS;
+    if (strcmp(e, "cols") == 0) return CPM_FWD_COLS;
+    return 0;
+  }();
+  return v;
+}
+
 int check_pyramid(const cpm_pyramid_t* p, const char* what) {
   CPM_CHECK_ARG(p != nullptr, "%s is NULL", what);
   CPM_CHECK_ARG(p->num_levels >= 1 && p->num_levels <= CPM_MAX_LEVELS, "%s: num_levels %d not in [1,%d]", what,
@@ -336,6 +356,17 @@ extern "C" int cpm_roi_align_forward_ex(const cpm_pyramid_t* feat, const void* d
                        (long)K * ((feat->channels + 63) / 64) < (1L << 31);
   const bool cols_ok = (nhwc_ok || bf16_ok) && interpolation == CPM_INTERP_BILINEAR &&
                        fwd_cols_supported(feat, pooled_h, pooled_w, sampling_ratio, d_out);
+  const bool rows_ok = nhwc_ok && pooled_layout == CPM_POOLED_KCHW &&
+                       fwd_rows_supported(feat, pooled_h, pooled_w, sampling_ratio, d_out);
+  if (impl == CPM_FWD_ROWS && !rows_ok) {
+    set_error("CPM_FWD_ROWS needs an NHWC fp32 pyramid, a (K,C,PH,PW) output, bilinear interpolation, a 7x7 or 14x14 pooler, "
+              "sampling_ratio 1 or 2, C %% 128 == 0 (7x7) / C %% 64 == 0 (14x14) and a driver with cuTensorMapEncodeTiled");
+    return CPM_ERR_UNSUPPORTED;
+  }
+  if (rows_ok && (impl == CPM_FWD_ROWS || (impl == CPM_FWD_AUTO && fwd_impl_env() != CPM_FWD_COLS))) {
+    rc = launch_fwd_rows(feat, pv, (const float*)d_rois, K, pooled_h, sampling_ratio, aligned, mp, d_roi_levels, (float*)d_out, st);
+    if (rc != CPM_ERR_UNSUPPORTED || impl == CPM_FWD_ROWS) return rc;
+  }
   if (impl == CPM_FWD_COLS && !cols_ok) {
     set_error("CPM_FWD_COLS needs an NHWC fp32 pyramid, bilinear interpolation, a 7x7 or 14x14 pooler, sampling_ratio 1 or 2 "
               "and C %% 128 == 0 (7x7) / C %% 64 == 0 (14x14)");

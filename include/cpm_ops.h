@@ -64,7 +64,9 @@ extern "C" {
 #define CPM_FWD_AUTO 0
 #define CPM_FWD_GENERIC 1         /* one thread per output element, any parameters / layout, fp32/fp64 */
 #define CPM_FWD_NHWC 2            /* general channel-vector gather (bilinear, NHWC, fp32, C % 4 == 0, any pooled size) */
-#define CPM_FWD_COLS 4            /* column-table kernel: 7x7 / 14x14 poolers, sampling_ratio 1|2, NHWC fp32 (AUTO's choice) */
+#define CPM_FWD_COLS 4            /* column-table kernel: 7x7 / 14x14 poolers, sampling_ratio 1|2, NHWC fp32 or bf16, either pooled layout */
+#define CPM_FWD_ROWS 8            /* row-streaming TMA kernel: same poolers, fp32, (K,C,PH,PW) output, <= 4 levels (AUTO's choice where it
+                                     applies; CPM_FWD_IMPL=cols in the environment makes AUTO take CPM_FWD_COLS instead) */
 
 /*
  * A feature pyramid (or the pyramid of dense feature gradients): L levels of dense maps that share batch
@@ -114,7 +116,7 @@ CPM_API int cpm_set_device(int device);
  * (K, C, PH, PW) -- one launch, no nonzero()/index_put, no device sync.
  *   d_rois      (K,5) [batch_idx, x1, y1, x2, y2], same dtype as the pyramid (ROIAlign_cuda.cu:381-382)
  *   mapper      ignored when num_levels == 1; d_roi_levels (optional, int32[K]) overrides the mapper
- *   impl        CPM_FWD_AUTO | CPM_FWD_GENERIC | CPM_FWD_NHWC | CPM_FWD_COLS
+ *   impl        CPM_FWD_AUTO | CPM_FWD_GENERIC | CPM_FWD_NHWC | CPM_FWD_COLS | CPM_FWD_ROWS
  * K == 0 is a no-op (ROIAlign_cuda.cu:401-404). */
 CPM_API int cpm_roi_align_forward(const cpm_pyramid_t* feat, const void* d_rois, int64_t K, int pooled_h, int pooled_w,
                           int sampling_ratio, int aligned, int interpolation, const cpm_level_mapper_t* mapper,

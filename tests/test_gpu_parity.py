@@ -143,11 +143,16 @@ def _size_sweep_rois(seed, B, img=(200, 336)):
     return torch.cat([rois, synthetic.adversarial_rois(img[0], img[1], B)], 0)
 
 
+FWD_KERNELS = [pytest.param(_lib.FWD_COLS, id="cols"), pytest.param(_lib.FWD_ROWS, id="rows")]
+
+
+@pytest.mark.parametrize("impl", FWD_KERNELS)
 @pytest.mark.parametrize("P,C", [(7, 128), (7, 256), (14, 64), (14, 256)])
 @pytest.mark.parametrize("sr,aligned", [(2, False), (1, False), (2, True)])
-def test_roi_align_cols_kernel(P, C, sr, aligned):
-    """The column-table forward kernel (CPM_FWD_COLS: 7x7 / 14x14, sampling_ratio 1|2) on every level scale, all RoI
-    size regimes, against the oracle and against the reference-shaped generic kernel."""
+def test_roi_align_cols_kernel(P, C, sr, aligned, impl):
+    """The two forward kernels of the CPM poolers (CPM_FWD_COLS: column tables; CPM_FWD_ROWS: TMA row streaming; 7x7 /
+    14x14, sampling_ratio 1|2) on every level scale, all RoI size regimes, against the oracle and against the
+    reference-shaped generic kernel."""
     B = 2
     gen = torch.Generator().manual_seed(100 + P + C + sr)
     feats = synthetic.pyramid(gen, B, C, 200, 336)
@@ -156,7 +161,7 @@ def test_roi_align_cols_kernel(P, C, sr, aligned):
         rois = rois[(rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])]
     for l in (0, 1, 3):
         f = feats[l].cuda().contiguous(memory_format=torch.channels_last)
-        out = pooler_forward([f], [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, impl=_lib.FWD_COLS)
+        out = pooler_forward([f], [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, impl=impl)
         gen_out = pooler_forward([f], [SCALES[l]], rois.cuda(), (P, P), sr, aligned, 0, None, impl=_lib.FWD_GENERIC)
         close(out.cpu(), gen_out.cpu())
         sub = slice(0, None, 3)       # the oracle is scalar C: check a third of the RoIs against it
@@ -164,22 +169,47 @@ def test_roi_align_cols_kernel(P, C, sr, aligned):
         close(out.cpu().numpy()[sub], ref)
 
 
+@pytest.mark.parametrize("impl", FWD_KERNELS)
 @pytest.mark.parametrize("P", [7, 14])
-def test_roi_align_cols_kernel_multilevel(P):
-    """Fused level mapping inside the column-table kernel: COCO-shaped RoIs over the 4-level pyramid, C = 256."""
+def test_roi_align_cols_kernel_multilevel(P, impl):
+    """Fused level mapping inside the kernel: COCO-shaped RoIs over the 4-level pyramid, C = 256."""
     B, C = 2, 256
     gen = torch.Generator().manual_seed(77)
     feats = synthetic.pyramid(gen, B, C, 200, 336)
     rois = torch.cat([synthetic.coco_like_rois(gen, 64, B, 200, 336), _size_sweep_rois(5, B)], 0)
     xs = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
     m = _lib.make_mapper(2, 5)
-    out = pooler_forward(xs, SCALES, rois.cuda(), (P, P), 2, False, 0, m, impl=_lib.FWD_COLS)
+    out = pooler_forward(xs, SCALES, rois.cuda(), (P, P), 2, False, 0, m, impl=impl)
     levels = oracle.level_map(rois.numpy(), 2, 5)
     ref = np.zeros(out.shape, np.float32)
     for l in range(4):
         idx = np.nonzero(levels == l)[0]
         ref[idx] = oracle.roi_align_forward(feats[l].numpy(), rois.numpy()[idx], SCALES[l], P, P, 2, False)
     close(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("P", [7, 14])
+def test_roi_align_rows_kernel_special_footprints(P):
+    """CPM_FWD_ROWS outside its streaming scheme and at its edges: row segments wider than 48 pixels and footprints taller
+    than 128 rows (pooled by the in-kernel direct gather), 41..48-pixel segments (6 chunks, one or two ring slots), RoIs of
+    negative height with aligned = true, RoIs that leave the map, a bad image index (zeros), bit-identical repeats; the
+    library's own choice (CPM_FWD_AUTO) is this kernel and gives the same bits."""
+    gen = torch.Generator().manual_seed(41 + P)
+    fh = torch.randn(2, 128, 300, 90, generator=gen)
+    f = fh.cuda().contiguous(memory_format=torch.channels_last)
+    rois = torch.tensor([[0, 0, 0, 89, 299], [1, 3, 5, 60, 280], [0, 10, 10, 40, 250], [1, 20.5, 30.25, 33, 47],
+                         [0, 0, 0, 47, 20], [1, 2, 100, 44.5, 140], [0, 40, 200, 80, 120], [1, -30, -40, 20, 30],
+                         [0, 70, 280, 120, 330], [1, 500, 500, 600, 600], [0, 12.3, 7.7, 12.3, 7.7]], dtype=torch.float32)
+    for aligned in (False, True):
+        out = pooler_forward([f], [1.0], rois.cuda(), (P, P), 2, aligned, 0, None, impl=_lib.FWD_ROWS)
+        again = pooler_forward([f], [1.0], rois.cuda(), (P, P), 2, aligned, 0, None, impl=_lib.FWD_ROWS)
+        auto = pooler_forward([f], [1.0], rois.cuda(), (P, P), 2, aligned, 0, None)
+        assert torch.equal(out, again) and torch.equal(out, auto)
+        ref = oracle.roi_align_forward(fh.numpy(), rois.numpy(), 1.0, P, P, 2, aligned)
+        close(out.cpu().numpy(), ref)
+    bad = torch.tensor([[0, 2, 2, 40, 30], [5, 2, 2, 40, 30], [-1, 2, 2, 40, 30]], dtype=torch.float32).cuda()
+    out = pooler_forward([f], [1.0], bad, (P, P), 2, False, 0, None, impl=_lib.FWD_ROWS)
+    assert float(out[0].abs().max()) > 0 and float(out[1:].abs().max()) == 0.0
 
 
 def test_roi_align_nearest_and_errors():
@@ -622,10 +652,13 @@ def test_pooled_channels_last_matches_contiguous(P, C):
     rois = torch.cat([synthetic.coco_like_rois(gen, 40, B, 200, 336), _size_sweep_rois(3, B)], 0).cuda()
     xs = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
     m = _lib.make_mapper(2, 5)
-    a = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m)
+    # (the channels_last output comes from the column-table kernel; the library's default for the reference layout is the
+    # row-streaming kernel, same values to rounding)
+    a = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m, impl=_lib.FWD_COLS)
     b = pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m, channels_last=True)
     assert a.is_contiguous() and b.is_contiguous(memory_format=torch.channels_last) and not b.is_contiguous()
     assert torch.equal(a, b)
+    close(pooler_forward(xs, SCALES, rois, (P, P), 2, False, 0, m).cpu(), a.cpu())
     go = torch.randn(a.shape, generator=gen).cuda()
     shapes = [tuple(f.shape) for f in feats]
     ga = pooler_backward(go, shapes, SCALES, rois, (P, P), 2, False, 0, m)
