@@ -337,8 +337,9 @@ roi_align_fwd_rows(const __grid_constant__ Maps maps, PyramidView pv, const floa
   const int rowbytes = nch * K_::kChunkBytes;
   const int slotbytes = 2 * rowbytes;
   const int nslots = min(kMaxSlots, K_::kRingBytes / slotbytes);
-  const uint32_t ring_s = smem_u32(smem_raw + K_::kTileBytes);
-  const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty);
+  // (opaque to the compiler: it would otherwise rebuild these shared-window addresses from %cluster_ctaid at every use)
+  uint32_t ring_s = smem_u32(smem_raw + K_::kTileBytes), full_s = smem_u32(full), empty_s = smem_u32(empty);
+  asm volatile("" : "+r"(ring_s), "+r"(full_s), "+r"(empty_s));
   const uint32_t bar_end = (uint32_t)(nslots * 8);
 
   if (warp == 7) {

@@ -56,7 +56,7 @@ if "--json" in ARGS:
     JSON_OUT = ARGS[i + 1]
     ARGS = ARGS[:i] + ARGS[i + 2:]
 DRAM = {}
-OPKEY = (("roi_align_fwd_cols<1", "fwd7"), ("roi_align_fwd_cols<2", "fwd14"), ("bwd_tiles_staged<0, 7, 2>", "bwd7"),
+OPKEY = (("roi_align_fwd_rows<1", "fwd7"), ("roi_align_fwd_rows<2", "fwd14"), ("roi_align_fwd_cols<1", "fwd7"), ("roi_align_fwd_cols<2", "fwd14"), ("bwd_tiles_staged<0, 7, 2>", "bwd7"),
          ("bwd_tiles_staged<0, 14, 2>", "bwd14"), ("bwd_tiles_staged<0,7,2>", "bwd7"), ("bwd_tiles_staged<0,14,2>", "bwd14"),
          ("stage_pyramid_f32", "stage"))
 
