@@ -143,6 +143,9 @@ struct Cfg {
   static constexpr int SK = NG == 1 ? 0 : 4;      // tile skew (floats) per 4 channels: 2-way instead of 8-way store conflicts
   static constexpr int kTileBytes = ((CH * PP + SK * QL) * 4 + 127) & ~127;
   static constexpr int kChunkBytes = 8 * CH * 4;  // one TMA box: 8 pixels x CH channels
+#ifndef FWDR_CTAS1
+#define FWDR_CTAS1 2
+#endif
 #ifndef FWDR_RING1
 #define FWDR_RING1 20
 #endif
@@ -151,6 +154,7 @@ struct Cfg {
 #endif
   static constexpr int kRingBytes = (NG == 1 ? FWDR_RING1 : FWDR_RING2) * kChunkBytes;    // 80 KB / 56 KB: two CTAs per SM
   static constexpr int kSmemBytes = kTileBytes + kRingBytes;
+  static_assert(kRingBytes >= 2 * kMaxChunks * kChunkBytes, "the ring must hold one pair of the widest rows");
 };
 
 // index of bit `i` among the set bits of the 128-bit mask m
@@ -249,7 +253,7 @@ __device__ __noinline__ void pool_direct(const float* __restrict__ level, int H,
 }
 
 template <int NG, int G>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NG == 1 ? FWDR_CTAS1 : 2)
 roi_align_fwd_rows(const __grid_constant__ Maps maps, PyramidView pv, const float* __restrict__ rois, int aligned, MapperView mp,
                    const int* __restrict__ roi_levels, float* __restrict__ out, int chunks, int cpc) {
   typedef Cfg<NG> K_;
