@@ -354,6 +354,22 @@ __global__ void __launch_bounds__(256) bwd_prepare(PyramidView pv, const float* 
 //   - accumulates  g[y][x][c] += sum_q WX[q][x] * (sum_p WY[y][p] * S[p][q][c])  in registers (packed FFMA2), vertical
 //     combine first, in a fixed order: deterministic, no atomics.
 namespace bst {
+#ifndef BWD_TRACE
+#define BWD_TRACE 0
+#endif
+#if BWD_TRACE
+__device__ unsigned long long g_btrace[8192 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define BTR(i) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_btrace[blockIdx.x * 8 + (i)] = gtime(); } while (0)
+#define BTRV(i, v) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_btrace[blockIdx.x * 8 + (i)] = (unsigned long long)(v); } while (0)
+#else
+#define BTR(i)
+#define BTRV(i, v)
+#endif
 
 // Bins per staging buffer.  48 rather than 56: at 62 KB per CTA three CTAs fit the 196 KB shared-memory carve-out, which
 // leaves the SM a 60 KB L1 instead of 28 KB -- the 4-byte transposing copies of a (K,C,PH,PW) gradient hit it (neighbouring
@@ -444,6 +460,8 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
   const float invG = 1.0f / (float)G;
   const int y = y0 + warp;
 
+  BTR(0);
+  int n_items = 0;
   u64 acc[TW][2];
 #pragma unroll
   for (int x = 0; x < TW; x++) acc[x][0] = acc[x][1] = 0ull;
@@ -669,6 +687,7 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
       }
     };
 
+    if (base == 0) BTR(1);
     if (threadIdx.x == 0) {
       generate(sm.ring[0]);
       generate(sm.ring[1]);
@@ -686,9 +705,11 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
       compute(cur, bf);
       cur = nxt;
       bf ^= 1;
+      n_items++;
     }
     __syncthreads();
   }
+  BTR(2);
 
   // ---- the tile's gradient: written exactly once ----
   if (active && y < H) {
@@ -728,7 +749,20 @@ bwd_tiles_staged(PyramidView pv, TileGrid tg, const float* __restrict__ go, cons
         if (x0 + x < W) dst[x * C4] = make_ulonglong2(acc[x][0], acc[x][1]);
     }
   }
+  BTR(3);
+  BTRV(4, n_items);
+  BTRV(5, pc);
 }
+
+#if BWD_TRACE
+}  // namespace bst
+}  // namespace cpm
+extern "C" __attribute__((visibility("default"))) int cpm_debug_bwd_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, cpm::bst::g_btrace, sizeof(unsigned long long) * n);
+}
+namespace cpm {
+namespace bst {
+#endif
 
 typedef void (*StagedFn)(PyramidView, TileGrid, const float*, const TapS*, const int4*, int, int, int, int, const int*,
                          const int*, int, const int*, const int2*);
