@@ -375,6 +375,98 @@ def bench_config0(dev):
     return res
 
 
+def bench_config4(dev, ra):
+    """configs[4], op-level proxy (the model itself -- X-101-64x4d-FPN-DCN -- is out of scope): the
+    inference-side use of the path on one rank: 2 images x 1000 RoIs/img, NCHW maps in, 7x7 box-head pooling and 14x14
+    grid-head pooling forward only, staging of the pyramid inside the timed graph; the reference's own CUDA kernels through
+    its per-level loop beside it."""
+    from cpm_r_cnn_b200 import _lib, synthetic as sy
+    from cpm_r_cnn_b200.roi_align import pooler_forward
+    res = {}
+    gen = torch.Generator().manual_seed(4)
+    B, R = IMGS_PER_GPU, 1000
+    rois_h = sy.coco_like_rois(gen, R, B)
+    feats_h = sy.pyramid(gen, B, CHANNELS)
+    feats = [f.to(dev) for f in feats_h]
+    rois = rois_h.to(dev)
+    scales = list(sy.FPN_SCALES)
+    mapper = _lib.make_mapper(2, 5)
+
+    def step():
+        ra.STAGING_CACHE.clear()
+        return [pooler_forward(feats, scales, rois, p, SAMPLING, False, 0, mapper) for p in POOLERS]
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    g, _ = capture(step)
+    ms = time_graphs([g], 10)[0]
+    res["ours"] = {"ms": ms, "rois_per_sec": 2 * B * R / (ms * 1e-3), "rois": B * R,
+                   "note": "7x7 + 14x14 forward, NCHW in, NHWC staging inside; RoI-units = RoIs x 2 poolers"}
+    try:
+        from oracle import build_ref
+        ref = build_ref.load("pet_ref_cuda")
+        lv = sy.fpn_levels_host(rois_h).to(dev)
+
+        def ref_step():
+            outs = []
+            for p in POOLERS:
+                out = torch.zeros((B * R, CHANNELS, p[0], p[1]), device=dev)
+                for l, f in enumerate(feats):
+                    idx = torch.nonzero(lv == l).squeeze(1)       # poolers.py:127-130 (host sync included)
+                    out[idx] = ref.roi_align_forward(f, rois[idx], scales[l], p[0], p[1], SAMPLING, False, 0)
+                outs.append(out)
+            return outs
+
+        for _ in range(2):
+            ref_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ref_step()
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1) / 5
+        res["reference_gpu"] = {"ms": rms, "rois_per_sec": 2 * B * R / (rms * 1e-3),
+                                "op": "unmodified ROIAlign_cuda.cu through the reference Pooler's per-level loop"}
+        res["speedup_vs_reference_gpu"] = rms / ms
+    except Exception as ex:
+        res["reference_gpu"] = {"unavailable": repr(ex)[:200]}
+    return res
+
+
+def bench_allreduce(dev, world, dist, sync_all):
+    """configs[3], the collective of the surrounding training step (north_star: NCCL is used only for DDP's gradient
+    all-reduce, never inside the ops): one all-reduce of a gradient set the size of R-101-FPN CPM R-CNN's (~62 M fp32
+    parameters, 25 MB buckets as DDP would issue them), timed on the device, max over ranks."""
+    if world <= 1:
+        return {}
+    n_params, bucket = 62_000_000, 25 * 1024 * 1024 // 4
+    bufs = [torch.zeros(min(bucket, n_params - i), device=dev) for i in range(0, n_params, bucket)]
+
+    def step():
+        for b in bufs:
+            dist.all_reduce(b)
+
+    for _ in range(3):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        step()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    nbytes = 4 * n_params
+    return {"ms": ms, "bytes": nbytes, "buckets": len(bufs), "algbw_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "busbw_gbs": nbytes / (ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+            "note": "NCCL all-reduce of a 62 M-parameter fp32 gradient set in 25 MB buckets (what DDP adds around the ops)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import cpm_r_cnn_b200 as ops
@@ -679,6 +771,9 @@ def run_ours(args):
     gtg = bench_grid_targets(ops, dev, rank)
     mat = bench_matcher(ops, dev, rank)
     cfg0 = bench_config0(dev) if rank == 0 and "config0" not in skip else {}
+    cfg4 = bench_config4(dev, ra) if rank == 0 and "config4" not in skip else {}
+    sync_all()
+    ddp = bench_allreduce(dev, world, dist, sync_all) if "allreduce" not in skip else {}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -754,7 +849,8 @@ def run_ours(args):
                                              "note": "the case a head inside a resident model sees: pyramid and its gradient stay "
                                                      "on the device; RoIs + pooled gradients up, pooled outputs down"}},
                 "gpu_launches": int(launches), "clocks": clocks, "nms": nms, "grid_decode": decode, "rpn_proposals": rpn,
-                "detection_postprocess": det, "grid_targets": gtg, "iou_matcher": mat, "config0": cfg0}
+                "detection_postprocess": det, "grid_targets": gtg, "iou_matcher": mat, "config0": cfg0,
+                "config4_inference_proxy": cfg4, "config3_ddp_allreduce": ddp}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": cpu_sample,
                                     "seconds": cpu_dt}
