@@ -1257,3 +1257,28 @@ def test_level2_C_module_against_the_reference_build():
     boxes, scores, segs, labels, img = synthetic.detection_candidates(g, 1, 300, 80)
     assert torch.equal(C.ml_nms(boxes.cuda(), scores.cuda(), labels.cuda(), 0.3, 0),
                        ref.ml_nms(boxes.cuda(), scores.cuda(), labels.cuda(), 0.3, 0))
+
+
+def test_rows_forward_is_repeatable_under_load():
+    """The row-streaming forward synchronises through mbarriers only (a ring of TMA row slots, a producer warp): a missing
+    wait shows up as run-to-run differences when the timing moves.  40 forwards of a 2 x 256-RoI workload while a second
+    stream keeps the SMs busy with backward kernels: every output bit-identical to the first, and equal to the column-table
+    kernel within the parity bound."""
+    gen = torch.Generator().manual_seed(123)
+    B, C = 2, 256
+    feats = [f.cuda().contiguous(memory_format=torch.channels_last) for f in synthetic.pyramid(gen, B, C, 400, 672)]
+    rois = torch.cat([synthetic.coco_like_rois(gen, 256, B, 400, 672), _size_sweep_rois(17, B, (400, 672))], 0).cuda()
+    m = _lib.make_mapper(2, 5)
+    shapes = [tuple(f.shape) for f in feats]
+    side = torch.cuda.Stream()
+    for P in (7, 14):
+        first = pooler_forward(feats, SCALES, rois, (P, P), 2, False, 0, m, impl=_lib.FWD_ROWS)
+        go = torch.randn(first.shape, generator=gen).cuda()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for _ in range(12):
+                pooler_backward(go, shapes, SCALES, rois, (P, P), 2, False, 0, m)
+        outs = [pooler_forward(feats, SCALES, rois, (P, P), 2, False, 0, m, impl=_lib.FWD_ROWS) for _ in range(40)]
+        torch.cuda.synchronize()
+        assert all(torch.equal(first, o) for o in outs)
+        close(first.cpu(), pooler_forward(feats, SCALES, rois, (P, P), 2, False, 0, m, impl=_lib.FWD_COLS).cpu())
