@@ -27,6 +27,14 @@ class Pyramid(ctypes.Structure):
                 ("width", ctypes.c_int32 * CPM_MAX_LEVELS), ("spatial_scale", ctypes.c_float * CPM_MAX_LEVELS)]
 
 
+class RpnLevels(ctypes.Structure):
+    _fields_ = [("num_levels", ctypes.c_int32), ("num_images", ctypes.c_int32), ("row", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("d_objectness", ctypes.c_void_p * CPM_MAX_LEVELS),
+                ("d_regression", ctypes.c_void_p * CPM_MAX_LEVELS), ("d_anchors", ctypes.c_void_p * CPM_MAX_LEVELS),
+                ("anchors_per_image", ctypes.c_int32 * CPM_MAX_LEVELS), ("A", ctypes.c_int32 * CPM_MAX_LEVELS),
+                ("HW", ctypes.c_int32 * CPM_MAX_LEVELS), ("k", ctypes.c_int32 * CPM_MAX_LEVELS)]
+
+
 class LevelMapperC(ctypes.Structure):
     _fields_ = [("k_min", ctypes.c_float), ("k_max", ctypes.c_float), ("canonical_scale", ctypes.c_float),
                 ("canonical_level", ctypes.c_float), ("eps", ctypes.c_float)]
@@ -77,6 +85,11 @@ _SIGNATURES = {
     "cpm_rpn_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "cpm_rpn_flatten_objectness": (ctypes.c_int, [ctypes.POINTER(RpnLevels), ctypes.c_void_p, ctypes.c_void_p]),
+    "cpm_rpn_select_decode": (ctypes.c_int, [ctypes.POINTER(RpnLevels), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                             ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "cpm_grid_targets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int32), ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]),

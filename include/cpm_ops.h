@@ -219,6 +219,31 @@ CPM_API int cpm_rpn_decode(const float* d_deltas, const float* d_anchors, const 
                    const float* weights, float bbox_xform_clip, float min_size, float* d_boxes, int32_t* d_segments_out,
                    void* stream);
 
+/* All FPN levels of RPNPostProcessor.forward (rpn/inference.py:115-143) in two launches around ONE top-k:
+ *   cpm_rpn_flatten_objectness: rows (L*N, row) fp32, row l*N+n = permute_and_flatten (utils/misc.py:6-10) of level l's
+ *     objectness logits (N, A, H, W) for image n, i.e. index hw*A + a, padded with -inf up to `row` -- the caller applies
+ *     sigmoid and one top-k (k = max_l k[l], sorted) to the rows (inference.py:84-88 for every level at once);
+ *   cpm_rpn_select_decode: for level l, image n, rank j < k[l], in that order (output index first[l] + n*k[l] + j with
+ *     first[l] = N * sum_{l' < l} k[l']): the winner's deltas from the (N, 4A, H, W) regression output, its anchor
+ *     (d_anchors[l] is (H*W*A, 4), or (N, H*W*A, 4) when anchors_per_image[l]), then cpm_rpn_decode's arithmetic against
+ *     d_image_wh (N,2); d_scores = the top-k values; segments = l*N + n or a trash segment (too small, or a padding winner).
+ *   M = N * sum_l k[l] outputs; feed boxes / scores / segments to cpm_nms_batched with L*N + num_trash segments. */
+typedef struct {
+  int32_t num_levels, num_images;
+  int32_t row;                                  /* padded row length, >= max_l A[l]*HW[l] */
+  int32_t reserved;
+  const float* d_objectness[CPM_MAX_LEVELS];    /* (N, A, H, W) fp32 contiguous */
+  const float* d_regression[CPM_MAX_LEVELS];    /* (N, 4A, H, W) fp32 contiguous */
+  const float* d_anchors[CPM_MAX_LEVELS];
+  int32_t anchors_per_image[CPM_MAX_LEVELS];
+  int32_t A[CPM_MAX_LEVELS], HW[CPM_MAX_LEVELS], k[CPM_MAX_LEVELS];
+} cpm_rpn_levels_t;
+CPM_API int cpm_rpn_flatten_objectness(const cpm_rpn_levels_t* levels, float* d_rows, void* stream);
+CPM_API int cpm_rpn_select_decode(const cpm_rpn_levels_t* levels, const int64_t* d_topk_idx, const float* d_topk_val,
+                          int64_t top_k, const float* d_image_wh, int64_t num_trash, const float* weights,
+                          float bbox_xform_clip, float min_size, float* d_boxes, float* d_scores, int32_t* d_segments_out,
+                          void* stream);
+
 /* ---- grid-point training targets (next row) ------------------------------------
  * Replaces GridLossComputation.prepare_target (grid_cascade_rcnn/loss.py:178-258: CPU triple loop + H2D).
  *   d_pos_boxes, d_gt_boxes (R,4) fp32: positive RoIs and their matched ground truth; sub_xy = HOST int32[P*2] sub-region
