@@ -574,29 +574,21 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// Tensor maps are a function of (pointer, shape, box): the levels of a pyramid are encoded once per host thread and reused
-// for as long as the same maps are pooled (the 5 poolers of a CPM iteration, every replay of a captured graph's launch).
-struct MapKey {
-  const void* ptr;
-  int C, W, H, B, CH, px;
+// Tensor maps are a function of (pointer, shape, box): the 24 maps of a pyramid (4 levels x 6 segment widths) are encoded once
+// per host thread and reused for as long as the same maps are pooled (the 5 poolers of a CPM iteration, steps whose tensors
+// recur at the same addresses, every replay of a captured graph's launch).
+struct PyramidKey {
+  const void* ptr[kMaxMapLevels];
+  int H[kMaxMapLevels], W[kMaxMapLevels];
+  int L, B, C, CH;
 };
-struct MapSlot {
-  MapKey key;
-  CUtensorMap map;
+struct PyramidMaps {
+  PyramidKey key;
+  Maps maps;
   bool used;
 };
 
-static int level_map(CUtensorMap* dst, const void* ptr, int C, int W, int H, int B, int CH, int px) {
-  static thread_local MapSlot cache[64];
-  static thread_local int next = 0;
-  for (int i = 0; i < 64; i++) {
-    const MapSlot& s = cache[i];
-    if (s.used && s.key.ptr == ptr && s.key.C == C && s.key.W == W && s.key.H == H && s.key.B == B && s.key.CH == CH &&
-        s.key.px == px) {
-      *dst = s.map;
-      return CPM_OK;
-    }
-  }
+static int encode_map(CUtensorMap* dst, const void* ptr, int C, int W, int H, int B, int CH, int px) {
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -606,20 +598,47 @@ static int level_map(CUtensorMap* dst, const void* ptr, int C, int W, int H, int
   const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
   const cuuint32_t box[4] = {(cuuint32_t)CH, (cuuint32_t)px, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMap tm;
-  const CUresult rc = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  const CUresult rc = enc(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc);
     return CPM_ERR_UNSUPPORTED;
   }
-  MapSlot& s = cache[next];
-  next = (next + 1) & 63;
-  s.key = MapKey{ptr, C, W, H, B, CH, px};
-  s.map = tm;
+  return CPM_OK;
+}
+
+static int pyramid_maps(const Maps** out, const cpm_pyramid_t* feat, int CH) {
+  static thread_local PyramidMaps cache[8];
+  static thread_local int next = 0;
+  PyramidKey key;
+  memset(&key, 0, sizeof(key));
+  key.L = feat->num_levels;
+  key.B = feat->batch;
+  key.C = feat->channels;
+  key.CH = CH;
+  for (int l = 0; l < feat->num_levels; l++) {
+    key.ptr[l] = feat->d_level[l];
+    key.H[l] = feat->height[l];
+    key.W[l] = feat->width[l];
+  }
+  for (int i = 0; i < 8; i++)
+    if (cache[i].used && memcmp(&cache[i].key, &key, sizeof(key)) == 0) {
+      *out = &cache[i].maps;
+      return CPM_OK;
+    }
+  PyramidMaps& s = cache[next];
+  s.used = false;
+  memset(&s.maps, 0, sizeof(s.maps));
+  for (int l = 0; l < feat->num_levels; l++)
+    for (int k = 0; k < kMaxChunks; k++)
+      if (int rc = encode_map(&s.maps.m[l][k], feat->d_level[l], feat->channels, feat->width[l], feat->height[l], feat->batch, CH,
+                              8 * (k + 1)))
+        return rc;
+  s.key = key;
   s.used = true;
-  *dst = tm;
+  next = (next + 1) & 7;
+  *out = &s.maps;
   return CPM_OK;
 }
 
@@ -671,14 +690,10 @@ bool fwd_rows_supported(const cpm_pyramid_t* feat, int pooled_h, int pooled_w, i
 
 int launch_fwd_rows(const cpm_pyramid_t* feat, const PyramidView& pv, const float* rois, long K, int P, int G, int aligned,
                     const MapperView& mp, const int* lv, float* out, cudaStream_t st) {
-  fwdr::Maps maps;
-  memset(&maps, 0, sizeof(maps));
   const int CH = P == 7 ? 128 : 64;
-  for (int l = 0; l < feat->num_levels; l++)
-    for (int k = 0; k < fwdr::kMaxChunks; k++)
-      if (int rc = fwdr::level_map(&maps.m[l][k], feat->d_level[l], feat->channels, feat->width[l], feat->height[l], feat->batch,
-                                   CH, 8 * (k + 1)))
-        return rc;
+  const fwdr::Maps* pm = nullptr;
+  if (int rc = fwdr::pyramid_maps(&pm, feat, CH)) return rc;
+  const fwdr::Maps& maps = *pm;
   if (P == 7) return G == 1 ? fwdr::launch_t<1, 1>(maps, pv, rois, K, aligned, mp, lv, out, st)
                             : fwdr::launch_t<1, 2>(maps, pv, rois, K, aligned, mp, lv, out, st);
   return G == 1 ? fwdr::launch_t<2, 1>(maps, pv, rois, K, aligned, mp, lv, out, st)
