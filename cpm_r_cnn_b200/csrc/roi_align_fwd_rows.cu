@@ -456,12 +456,16 @@ roi_align_fwd_rows(const __grid_constant__ Maps maps, PyramidView pv, const floa
     int pn = 0;
     u64 rlp = rl_lo;
     int next_last = (int)(rlp & 0xffull);
-    if (ci > 0) {             // the previous chunk's tile has left shared memory
-      if (issuer) bulk_wait_read();
-      bar_compute();
-    }
+    // the previous chunk's tile must have left shared memory before the first bin row of this one is stored -- not before
+    // its first feature rows are read: the wait sits in front of the first emission
+    bool tile_busy = ci > 0;
     auto emit = [&](const u64 (&w0)[2], const u64 (&w1)[2], const u64 (&w2)[2], const u64 (&w3)[2]) {
       // bin row pn from the window rows of age 0 (the row just finished) .. 3
+      if (tile_busy) {
+        if (issuer) bulk_wait_read();
+        bar_compute();
+        tile_busy = false;
+      }
       const float4 a = wap[pn];
       const u64 a0 = pack2(a.x, a.x), a1 = pack2(a.y, a.y), a2 = pack2(a.z, a.z), a3 = pack2(a.w, a.w);
       u64 ol = mul2(a0, w0[0]), oh = mul2(a0, w0[1]);
