@@ -421,17 +421,56 @@ roi_align_fwd_rows(const __grid_constant__ Maps maps, PyramidView pv, const floa
   const int quad = lane & (QL - 1);
   uint32_t xo[NTAP];
   u64 xw[NTAP];
+  // G = 2: when the four taps of every bin column fall on at most 3 consecutive pixels (sample spacing <= 1 pixel: bins up to
+  // 2 pixels wide), a thread reads 3 pixels per row with combined weights instead of 4 (a quarter less shared-memory traffic)
+  bool three = false;
+  if (G == 2) {
+    const int lo_o = __shfl_xor_sync(0xffffffffu, tx.lo, 1), hi_o = __shfl_xor_sync(0xffffffffu, tx.hi, 1);
+    const int cmin = min(tx.lo >= 0 ? tx.lo : 0x7fffffff, lo_o >= 0 ? lo_o : 0x7fffffff), cmax = max(tx.hi, hi_o);
+    three = __all_sync(0xffffffffu, cmax < 0 || cmax - cmin <= 2);
+  }
+  if (G == 2 && three) {
+    int col[4];
+    float wv[4];
 #pragma unroll
-  for (int i = 0; i < G; i++) {
-    const int src = q * G + i;
-    const int lo = __shfl_sync(0xffffffffu, tx.lo, src), hi = __shfl_sync(0xffffffffu, tx.hi, src);
-    const float wl = __shfl_sync(0xffffffffu, tx.wlo, src), wh = __shfl_sync(0xffffffffu, tx.whi, src);
-    const bool valid = lo >= 0;
-    xo[2 * i] = (uint32_t)((valid ? (lo - xlo) * CH * 4 : 0) + quad * 16);
-    xo[2 * i + 1] = (uint32_t)((valid ? (hi - xlo) * CH * 4 : 0) + quad * 16);
-    const float a = valid ? wl * kInvG : 0.f, b = valid ? wh * kInvG : 0.f;
-    xw[2 * i] = pack2(a, a);
-    xw[2 * i + 1] = pack2(b, b);
+    for (int i = 0; i < G; i++) {
+      const int src = q * G + i;
+      col[2 * i] = __shfl_sync(0xffffffffu, tx.lo, src);
+      col[2 * i + 1] = __shfl_sync(0xffffffffu, tx.hi, src);
+      const float wl = __shfl_sync(0xffffffffu, tx.wlo, src), wh = __shfl_sync(0xffffffffu, tx.whi, src);
+      const bool valid = col[2 * i] >= 0;
+      wv[2 * i] = valid ? wl * kInvG : 0.f;
+      wv[2 * i + 1] = valid ? wh * kInvG : 0.f;
+    }
+    int cmin = 0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < 4; e += 2)
+      if (col[e] >= 0) cmin = min(cmin, col[e]);
+    if (cmin == 0x7fffffff) cmin = xlo;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float w = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (col[e] >= 0 && col[e] == cmin + k) w += wv[e];
+      xo[k] = (uint32_t)((min(cmin + k, xhi) - xlo) * CH * 4 + quad * 16);
+      xw[k] = pack2(w, w);
+    }
+    xo[3] = xo[0];
+    xw[3] = 0ull;
+  } else {
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+      const int src = q * G + i;
+      const int lo = __shfl_sync(0xffffffffu, tx.lo, src), hi = __shfl_sync(0xffffffffu, tx.hi, src);
+      const float wl = __shfl_sync(0xffffffffu, tx.wlo, src), wh = __shfl_sync(0xffffffffu, tx.whi, src);
+      const bool valid = lo >= 0;
+      xo[2 * i] = (uint32_t)((valid ? (lo - xlo) * CH * 4 : 0) + quad * 16);
+      xo[2 * i + 1] = (uint32_t)((valid ? (hi - xlo) * CH * 4 : 0) + quad * 16);
+      const float a = valid ? wl * kInvG : 0.f, b = valid ? wh * kInvG : 0.f;
+      xw[2 * i] = pack2(a, a);
+      xw[2 * i + 1] = pack2(b, b);
+    }
   }
   // the completing rows of the 14 (7) bin rows, one byte each, in two registers; the window weights in the warp's table
   u64 rl_lo = 0ull, rl_hi = 0ull;
@@ -497,17 +536,21 @@ roi_align_fwd_rows(const __grid_constant__ Maps maps, PyramidView pv, const floa
           const uint32_t base2 = base + (two ? (uint32_t)rowbytes : 0u);
           ulonglong2 f[NTAP], g[NTAP];
 #pragma unroll
-          for (int k = 0; k < NTAP; k++) f[k] = lds128(base + xo[k]);
+          for (int k = 0; k < NTAP; k++)
+            if (k < 3 || !three) f[k] = lds128(base + xo[k]);
 #pragma unroll
-          for (int k = 0; k < NTAP; k++) g[k] = lds128(base2 + xo[k]);
+          for (int k = 0; k < NTAP; k++)
+            if (k < 3 || !three) g[k] = lds128(base2 + xo[k]);
           u64 tl = mul2(xw[0], f[0].x), th = mul2(xw[0], f[0].y);
           u64 sl = mul2(xw[0], g[0].x), sh = mul2(xw[0], g[0].y);
 #pragma unroll
           for (int k = 1; k < NTAP; k++) {
-            tl = fma2(xw[k], f[k].x, tl);
-            th = fma2(xw[k], f[k].y, th);
-            sl = fma2(xw[k], g[k].x, sl);
-            sh = fma2(xw[k], g[k].y, sh);
+            if (k < 3 || !three) {
+              tl = fma2(xw[k], f[k].x, tl);
+              th = fma2(xw[k], f[k].y, th);
+              sl = fma2(xw[k], g[k].x, sl);
+              sh = fma2(xw[k], g[k].y, sh);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_s(empty_s + bo);
