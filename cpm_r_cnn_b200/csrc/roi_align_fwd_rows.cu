@@ -7,18 +7,23 @@
 // (sample coordinates, validity and clamping exactly bilinear_interpolate's, :36-86, per axis).  roi_align_fwd_cols walks
 // that product bin row by bin row and re-reads every feature row once per bin row that taps it (L2 -> SM traffic 4-5x the
 // footprint).  Here the footprint streams through shared memory ONCE, row by row:
-//   CTA      = (RoI, channel chunk): 7 arithmetic warps + 1 producer warp.  The RoI's FPN level (LevelMapper,
-//              poolers.py:29-40) is computed in the kernel and selects the level's tensor map.
-//   producer = per tapped feature row (rows no sample touches are skipped), one cp.async.bulk.tensor.4d per 8-pixel chunk
-//              of the row segment [x_lo, x_hi] x CH channels of the NHWC map (UTMALDG; box {CH, 8, 1, 1}) into a ring of
-//              row slots, completing on the slot's `full` mbarrier; a slot is refilled when the 7 arithmetic warps have
-//              arrived on its `empty` mbarrier.
-//   thread   = (bin column q, 4 channels).  Its 2G x-taps (shared-memory offsets inside a row + weights) live in
-//              registers for the whole RoI.  Per row: 2G LDS.128 + packed FFMA2 -> T[y][q] in registers, kept in a
-//              4-row register window (a bin row's samples tap at most 4 consecutive tapped rows); when the last row of
-//              bin row p has passed, out[p][q] = sum_age wa[p][age] * window[age] goes to the shared-memory output tile.
-//              T never touches shared memory, nothing is exchanged between threads: no barrier in the loop.
-//   out      = the (channel, bin)-ordered tile leaves with cp.async.bulk (UBLKCP), as in roi_align_fwd_cols.
+//   CTA      = (RoI, 1-4 channel chunks of 128 / 64 channels): 7 arithmetic warps + 1 producer warp.  The RoI's FPN level
+//              (LevelMapper, poolers.py:29-40) is computed in the kernel and selects the level's tensor maps.  Every warp
+//              derives the RoI's geometry for itself (no table exchange: one __syncthreads in the kernel, for the mbarrier
+//              init); the tables are built once per RoI and the row stream runs on across its channel chunks.
+//   producer = per PAIR of tapped feature rows (rows no sample touches are skipped), ONE cp.async.bulk.tensor.4d per row,
+//              issued by lane 0 (UTMALDG; box {CH, 8n, 1, 1} of the NHWC map, one tensor map per level and segment width
+//              8..48 pixels -- an instruction with per-lane operands would be replayed lane by lane), into a ring of slots,
+//              completing on the slot's `full` mbarrier; a slot is refilled when the 7 arithmetic warps have arrived on its
+//              `empty` mbarrier.  The producer starts fetching before the arithmetic warps have built their bin tables.
+//   thread   = (bin column q, 4 channels).  Its x-taps (shared-memory offsets inside a row + weights) live in registers for
+//              the whole RoI: 2G of them, or -- G = 2 and samples at most a pixel apart -- 3 pixels with combined weights.
+//              Per row: those LDS.128 + packed FFMA2 -> T[y][q] in registers (the two rows of a slot are two independent
+//              chains), kept in a 4-row register window (a bin row's samples tap at most 4 consecutive tapped rows); when
+//              the last row of bin row p has passed, out[p][q] = sum_age wa[p][age] * window[age] goes to the shared-memory
+//              output tile.  T never touches shared memory, nothing is exchanged between threads: no barrier in the loop.
+//   out      = the (channel, bin)-ordered tile leaves with cp.async.bulk (UBLKCP) per chunk; the next chunk waits for its
+//              shared-memory reads only in front of its first finished bin row.
 // A RoI whose footprint does not fit the scheme (row segment wider than 48 pixels, more than 128 rows between its first
 // and last tap, nothing valid) is pooled by the same CTA with the direct per-sample gather (reference arithmetic).
 #include <cuda.h>
